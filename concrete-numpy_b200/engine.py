@@ -1,0 +1,309 @@
+"""
+Device engine: thin Python layer over the C ABI.  PyTorch is used only for device buffers
+(`torch.empty(..., dtype=torch.int64, device=...)`, `.data_ptr()`) and for the current stream.
+
+Ciphertext tensors are `torch.int64` of shape `[E, k*N+1]` (bit pattern of the u64 torus words,
+mask first, body last) -- SURVEY.md Appendix A.1.
+"""
+
+from dataclasses import asdict, dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+DOM_SK_SMALL, DOM_SK_BIG = 1, 2
+
+
+@dataclass(frozen=True)
+class CryptoParams:
+    """One TFHE parameter set (the reference uses a single set per circuit because
+    `_update_bit_widths` forces one width on every encrypted value,
+    concrete/numpy/mlir/graph_converter.py:315-322)."""
+
+    p: int                 # message bits carried by every ciphertext (one extra padding bit)
+    n: int                 # small LWE dimension
+    k: int                 # GLWE dimension
+    N: int                 # polynomial size
+    pbs_level: int
+    pbs_base_log: int
+    ks_level: int
+    ks_base_log: int
+    lwe_std: float         # noise std of the small key (relative to q)
+    glwe_std: float        # noise std of the big key
+
+    @property
+    def big_dim(self) -> int:
+        return self.k * self.N
+
+    @property
+    def ct_words(self) -> int:
+        return self.k * self.N + 1
+
+    def to_dict(self):
+        return asdict(self)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def to_np_u64(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy().view(np.uint64)
+
+
+def from_np_u64(a: np.ndarray, device) -> torch.Tensor:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return torch.from_numpy(a.view(np.int64)).to(device, non_blocking=False)
+
+
+class KeySet:
+    """Device-resident secret + evaluation keys for one parameter set."""
+
+    def __init__(self, params: CryptoParams, device, seed: int, keep_std_bsk: bool = False):
+        self.params = params
+        self.device = torch.device(device)
+        self.seed = int(seed)
+        p = params
+        dev = self.device
+        with torch.cuda.device(dev):
+            st = _stream()
+            self.sk_small = torch.empty(p.n, dtype=torch.int64, device=dev)
+            self.sk_big = torch.empty(p.big_dim, dtype=torch.int64, device=dev)
+            _lib.call("fhe_keygen_lwe_secret", self.sk_small.data_ptr(), p.n, self.seed, DOM_SK_SMALL, st)
+            _lib.call("fhe_keygen_lwe_secret", self.sk_big.data_ptr(), p.big_dim, self.seed, DOM_SK_BIG, st)
+            self.ksk = torch.empty((p.big_dim, p.ks_level, p.n + 1), dtype=torch.int64, device=dev)
+            _lib.call("fhe_keygen_ksk", self.ksk.data_ptr(), self.sk_big.data_ptr(), p.big_dim,
+                      self.sk_small.data_ptr(), p.n, p.ks_level, p.ks_base_log, p.lwe_std, self.seed, st)
+            bsk_std = torch.empty((p.n, p.pbs_level, p.k + 1, p.k + 1, p.N), dtype=torch.int64, device=dev)
+            scratch = torch.empty(p.k * p.N + p.k + 8, dtype=torch.int32, device=dev)
+            _lib.call("fhe_keygen_bsk", bsk_std.data_ptr(), self.sk_small.data_ptr(), p.n,
+                      self.sk_big.data_ptr(), p.k, p.N, p.pbs_level, p.pbs_base_log, p.glwe_std,
+                      self.seed, scratch.data_ptr(), st)
+            self.bsk_std = bsk_std if keep_std_bsk else None
+            self.bsk_f = bsk_std_to_fourier(bsk_std, p)
+            torch.cuda.current_stream().synchronize()
+
+    # sizes reported through CompilationFeedback (reference server.py:296-350)
+    def secret_keys_bytes(self) -> int:
+        return 8 * (self.params.n + self.params.big_dim)
+
+    def bootstrap_keys_bytes(self) -> int:
+        p = self.params
+        return 8 * p.n * p.pbs_level * (p.k + 1) * (p.k + 1) * p.N
+
+    def keyswitch_keys_bytes(self) -> int:
+        p = self.params
+        return 8 * p.big_dim * p.ks_level * (p.n + 1)
+
+
+def bsk_std_to_fourier(bsk_std: torch.Tensor, p: CryptoParams) -> torch.Tensor:
+    """Standard-domain BSK -> Fourier BSK on device (layout owned by csrc/pbs.cu)."""
+    lib = _lib.load()
+    if lib.fhe_pbs_cluster_size(p.N, p.k, p.pbs_level) < 0:
+        raise _lib.FheError(f"PBS layout unsupported for N={p.N} k={p.k} level={p.pbs_level}")
+    elems = lib.fhe_bsk_fourier_elems(p.n, p.k, p.N, p.pbs_level)
+    out = torch.empty((elems, 2), dtype=torch.float64, device=bsk_std.device)
+    with torch.cuda.device(bsk_std.device):
+        _lib.call("fhe_bsk_to_fourier", out.data_ptr(), bsk_std.data_ptr(), p.n, p.k, p.N,
+                  p.pbs_level, p.pbs_base_log, _stream())
+    return out
+
+
+class EvalKeys:
+    """Evaluation keys only (what the server sees): Fourier BSK + KSK."""
+
+    def __init__(self, params: CryptoParams, bsk_f: torch.Tensor, ksk: torch.Tensor):
+        self.params = params
+        self.bsk_f = bsk_f
+        self.ksk = ksk
+
+    @staticmethod
+    def of(keyset: KeySet) -> "EvalKeys":
+        return EvalKeys(keyset.params, keyset.bsk_f, keyset.ksk)
+
+
+# ------------------------------------------------------------------ client side ----
+
+def encrypt(keyset: KeySet, messages: np.ndarray, first_index: int = 0, seed: Optional[int] = None) -> torch.Tensor:
+    """Encode `m << (63 - p)` and LWE-encrypt each message under the big key."""
+    p = keyset.params
+    dev = keyset.device
+    m = np.ascontiguousarray(np.asarray(messages).reshape(-1).astype(np.uint64))
+    pt = from_np_u64(m << np.uint64(63 - p.p), dev)
+    ct = torch.empty((m.size, p.ct_words), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("fhe_encrypt_lwe_batch", ct.data_ptr(), pt.data_ptr(), m.size, keyset.sk_big.data_ptr(),
+                  p.big_dim, p.glwe_std, keyset.seed if seed is None else int(seed), int(first_index), _stream())
+    return ct
+
+
+def decrypt(keyset: KeySet, ct: torch.Tensor, return_phase: bool = False):
+    """Decrypt `[E, kN+1]` ciphertexts to messages of p+1 bits (reference client.py:201 + A.2)."""
+    p = keyset.params
+    ct = ct.contiguous()
+    E = ct.numel() // p.ct_words
+    msg = torch.empty(E, dtype=torch.int64, device=ct.device)
+    phase = torch.empty(E, dtype=torch.int64, device=ct.device) if return_phase else None
+    with torch.cuda.device(ct.device):
+        _lib.call("fhe_decrypt_lwe_batch", _ptr(phase), msg.data_ptr(), ct.data_ptr(), E,
+                  keyset.sk_big.data_ptr(), p.big_dim, p.p, _stream())
+    if return_phase:
+        return to_np_u64(msg), to_np_u64(phase)
+    return to_np_u64(msg)
+
+
+def decrypt_small(keyset: KeySet, ct: torch.Tensor) -> np.ndarray:
+    """Phase of ciphertexts under the small key (test / noise measurement helper)."""
+    p = keyset.params
+    ct = ct.contiguous()
+    E = ct.numel() // (p.n + 1)
+    phase = torch.empty(E, dtype=torch.int64, device=ct.device)
+    with torch.cuda.device(ct.device):
+        _lib.call("fhe_decrypt_lwe_batch", phase.data_ptr(), None, ct.data_ptr(), E,
+                  keyset.sk_small.data_ptr(), p.n, p.p, _stream())
+    return to_np_u64(phase)
+
+
+def trivial(params: CryptoParams, messages: np.ndarray, device) -> torch.Tensor:
+    m = np.ascontiguousarray(np.asarray(messages).reshape(-1).astype(np.uint64))
+    pt = from_np_u64(m << np.uint64(63 - params.p), device)
+    ct = torch.empty((m.size, params.ct_words), dtype=torch.int64, device=device)
+    with torch.cuda.device(device):
+        _lib.call("fhe_trivial_lwe_batch", ct.data_ptr(), pt.data_ptr(), m.size, params.big_dim, _stream())
+    return ct
+
+
+# ------------------------------------------------------------------ server side ----
+
+def build_lut_accumulators(params: CryptoParams, tables: np.ndarray) -> np.ndarray:
+    """Expand `[T, 2^p]` integer tables into `[T, (k+1)*N]` GLWE accumulators:
+    every entry repeated N/2^p times, pre-rotated by half a box with negacyclic sign, outputs
+    encoded at bit 63-p.  Host-side (tables are compile-time constants of a circuit)."""
+    p, N, k = params.p, params.N, params.k
+    tables = np.asarray(tables)
+    T = tables.shape[0]
+    assert tables.shape[1] == (1 << p), (tables.shape, p)
+    box = N >> p
+    if box < 1:
+        raise ValueError(f"polynomial size {N} too small for {p}-bit tables")
+    vals = (tables.astype(np.int64).view(np.uint64)) << np.uint64(64 - (p + 1))
+    poly = np.repeat(vals, box, axis=1)                       # [T, N]
+    half = box // 2
+    rolled = np.concatenate([poly[:, half:], (np.uint64(0) - poly[:, :half])], axis=1)
+    out = np.zeros((T, (k + 1) * N), dtype=np.uint64)
+    out[:, k * N:] = rolled
+    return out
+
+
+def keyswitch(ev: EvalKeys, ct: torch.Tensor) -> torch.Tensor:
+    p = ev.params
+    ct = ct.contiguous()
+    E = ct.numel() // p.ct_words
+    out = torch.empty((E, p.n + 1), dtype=torch.int64, device=ct.device)
+    with torch.cuda.device(ct.device):
+        _lib.call("fhe_keyswitch_batch", out.data_ptr(), ct.data_ptr(), E, ev.ksk.data_ptr(), p.big_dim,
+                  p.n, p.ks_level, p.ks_base_log, _stream())
+    return out
+
+
+def bootstrap(ev: EvalKeys, ct_small: torch.Tensor, luts: torch.Tensor, lut_idx: Optional[torch.Tensor]) -> torch.Tensor:
+    p = ev.params
+    E = ct_small.numel() // (p.n + 1)
+    out = torch.empty((E, p.ct_words), dtype=torch.int64, device=ct_small.device)
+    with torch.cuda.device(ct_small.device):
+        _lib.call("fhe_pbs_batch", out.data_ptr(), ct_small.data_ptr(), E, ev.bsk_f.data_ptr(),
+                  luts.data_ptr(), _ptr(lut_idx), p.n, p.k, p.N, p.pbs_level, p.pbs_base_log, _stream())
+    return out
+
+
+def table_lookup(ev: EvalKeys, ct: torch.Tensor, luts: torch.Tensor, lut_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """FHE.apply_lookup_table = keyswitch + programmable bootstrap per element."""
+    return bootstrap(ev, keyswitch(ev, ct), luts, lut_idx)
+
+
+def _rows(t: torch.Tensor, L: int) -> int:
+    return t.numel() // L
+
+
+def lin_add(a, b, L, ia=None, ib=None, E=None):
+    E = _rows(a, L) if E is None else E
+    out = torch.empty((E, L), dtype=torch.int64, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.call("fhe_lin_add", out.data_ptr(), a.data_ptr(), b.data_ptr(), _ptr(ia), _ptr(ib), E, L, _stream())
+    return out
+
+
+def lin_sub(a, b, L, ia=None, ib=None, E=None):
+    E = _rows(a, L) if E is None else E
+    out = torch.empty((E, L), dtype=torch.int64, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.call("fhe_lin_sub", out.data_ptr(), a.data_ptr(), b.data_ptr(), _ptr(ia), _ptr(ib), E, L, _stream())
+    return out
+
+
+def lin_neg(a, L, ia=None, E=None):
+    E = _rows(a, L) if E is None else E
+    out = torch.empty((E, L), dtype=torch.int64, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.call("fhe_lin_neg", out.data_ptr(), a.data_ptr(), _ptr(ia), E, L, _stream())
+    return out
+
+
+def lin_add_plain(a, pt, L, ia=None):
+    """pt: int64 tensor [E] of already-encoded plaintexts."""
+    E = pt.numel()
+    out = torch.empty((E, L), dtype=torch.int64, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.call("fhe_lin_add_plain", out.data_ptr(), a.data_ptr(), _ptr(ia), pt.data_ptr(), E, L, _stream())
+    return out
+
+
+def lin_plain_sub(a, pt, L, ia=None):
+    E = pt.numel()
+    out = torch.empty((E, L), dtype=torch.int64, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.call("fhe_lin_plain_sub", out.data_ptr(), a.data_ptr(), _ptr(ia), pt.data_ptr(), E, L, _stream())
+    return out
+
+
+def lin_mul_clear(a, c, L, ia=None):
+    """c: int64 tensor [E] of clear signed multipliers."""
+    E = c.numel()
+    out = torch.empty((E, L), dtype=torch.int64, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.call("fhe_lin_mul_clear", out.data_ptr(), a.data_ptr(), _ptr(ia), c.data_ptr(), E, L, _stream())
+    return out
+
+
+def lin_gather_mac(x, idx, w, L, bias=None):
+    """out[e] = sum_j w[e, j] * x[idx[e, j]] (+ bias[e] on the body); idx int32 [E, K], w int64 [E, K]."""
+    E, K = idx.shape
+    out = torch.empty((E, L), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("fhe_lin_gather_mac", out.data_ptr(), x.data_ptr(), idx.data_ptr(), w.data_ptr(), _ptr(bias),
+                  E, K, L, _stream())
+    return out
+
+
+def matmul_ct_clear(x, W, Mr, K, Nc, L):
+    """x: [Mr, K, L] ciphertexts, W: int64 [K, Nc] clear weights -> [Mr, Nc, L]."""
+    out = torch.empty((Mr * Nc, L), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("fhe_matmul_ct_clear", out.data_ptr(), x.data_ptr(), W.data_ptr(), Mr, K, Nc, L, _stream())
+    return out
+
+
+def measure_fp64_peak(device) -> float:
+    import ctypes as C
+
+    v = C.c_double(0.0)
+    with torch.cuda.device(device):
+        _lib.call("fhe_measure_fp64_peak", C.byref(v), _stream())
+    return float(v.value)

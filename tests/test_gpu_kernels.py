@@ -1,0 +1,202 @@
+"""GPU parity tests of the kernels behind the C ABI against the CPU oracle (same seeded inputs).
+
+Integer / byte work (keygen, encryption, keyswitch, linear ops) must be BIT-EXACT.
+The programmable bootstrap runs an fp64 FFT: its outputs must decrypt to the exact table value and
+stay within a stated torus distance of the oracle's output on the same inputs (tolerance below).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from concrete_numpy_b200 import engine as E
+from concrete_numpy_b200 import _lib
+
+
+def small_params(**kw):
+    base = dict(p=3, n=48, k=1, N=512, pbs_level=2, pbs_base_log=10, ks_level=4, ks_base_log=4,
+                lwe_std=2.0 ** -30, glwe_std=2.0 ** -45)
+    base.update(kw)
+    return E.CryptoParams(**base)
+
+
+def oracle_keys(oracle, p, seed):
+    sk_s = oracle.keygen_lwe_secret(p.n, seed, 1)
+    sk_b = oracle.keygen_lwe_secret(p.k * p.N, seed, 2)
+    return sk_s, sk_b
+
+
+@pytest.mark.parametrize("k,N", [(1, 512), (2, 256), (1, 1024)])
+def test_keygen_bit_exact(oracle, cuda_device, k, N):
+    p = small_params(k=k, N=N, n=40)
+    ks = E.KeySet(p, cuda_device, seed=1234, keep_std_bsk=True)
+    sk_s, sk_b = oracle_keys(oracle, p, 1234)
+    assert np.array_equal(E.to_np_u64(ks.sk_small), sk_s)
+    assert np.array_equal(E.to_np_u64(ks.sk_big), sk_b)
+    ksk = oracle.keygen_ksk(sk_b, sk_s, p.ks_level, p.ks_base_log, p.lwe_std, 1234)
+    assert np.array_equal(E.to_np_u64(ks.ksk), ksk)
+    bsk = oracle.keygen_bsk(sk_s, sk_b, p.k, p.N, p.pbs_level, p.pbs_base_log, p.glwe_std, 1234)
+    assert np.array_equal(E.to_np_u64(ks.bsk_std), bsk)
+
+
+def test_encrypt_decrypt_bit_exact(oracle, cuda_device):
+    p = small_params()
+    ks = E.KeySet(p, cuda_device, seed=7)
+    _, sk_b = oracle_keys(oracle, p, 7)
+    rng = np.random.default_rng(0)
+    m = rng.integers(0, 1 << p.p, 300).astype(np.uint64)
+    ct = E.encrypt(ks, m, first_index=11, seed=99)
+    ref = oracle.encrypt(m << np.uint64(63 - p.p), sk_b, p.glwe_std, 99, first_index=11)
+    assert np.array_equal(E.to_np_u64(ct), ref)
+    msg, phase = E.decrypt(ks, ct, return_phase=True)
+    assert np.array_equal(phase, oracle.decrypt_phase(ref, sk_b))
+    assert np.array_equal(msg, m)
+    # empty batch
+    assert E.encrypt(ks, np.zeros(0, dtype=np.uint64)).shape[0] == 0
+    # trivial ciphertexts
+    tv = E.trivial(p, m[:5], cuda_device)
+    assert np.array_equal(E.to_np_u64(tv), oracle.trivial(m[:5] << np.uint64(63 - p.p), p.big_dim))
+
+
+@pytest.mark.parametrize("B", [1, 5, 33, 600])
+@pytest.mark.parametrize("kN,n,level,base_log", [(512, 48, 4, 4), (1024, 97, 5, 3), (600, 130, 2, 9)])
+def test_keyswitch_bit_exact(oracle, cuda_device, B, kN, n, level, base_log):
+    rng = np.random.default_rng(B * 131 + kN)
+    ksk = rng.integers(0, 1 << 64, (kN, level, n + 1), dtype=np.uint64)
+    ct = rng.integers(0, 1 << 64, (B, kN + 1), dtype=np.uint64)
+    out = torch.empty((B, n + 1), dtype=torch.int64, device=cuda_device)
+    d_ksk, d_ct = E.from_np_u64(ksk, cuda_device), E.from_np_u64(ct, cuda_device)
+    _lib.call("fhe_keyswitch_batch", out.data_ptr(), d_ct.data_ptr(), B, d_ksk.data_ptr(), kN, n, level,
+              base_log, torch.cuda.current_stream().cuda_stream)
+    assert np.array_equal(E.to_np_u64(out), oracle.keyswitch(ct, ksk, level, base_log))
+
+
+def _negacyclic_sparse(a_pos, a_val, b):
+    N = b.size
+    out = np.zeros(N, dtype=np.uint64)
+    for pos, val in zip(a_pos, a_val):
+        rolled = np.concatenate([np.uint64(0) - b[N - pos:], b[:N - pos]]) if pos else b.copy()
+        out += rolled * np.uint64(val & 0xFFFFFFFFFFFFFFFF)
+    return out
+
+
+@pytest.mark.parametrize("N,k,level", [(256, 1, 1), (512, 2, 2), (2048, 1, 1), (4096, 1, 2), (8192, 1, 2),
+                                       (16384, 1, 2), (32768, 1, 2)])
+def test_fft_polymul(cuda_device, N, k, level):
+    """fp64 negacyclic FFT product == exact integer product (sparse small multiplier), to fp64
+    rounding: |err| <= 2^(64-53) * |a|_1 * 2^6."""
+    lib = _lib.load()
+    C = lib.fhe_pbs_cluster_size(N, k, level)
+    assert C >= 1
+    rng = np.random.default_rng(N)
+    npoly = 3
+    a = np.zeros((npoly, N), dtype=np.int64)
+    b = rng.integers(0, 1 << 64, (npoly, N), dtype=np.uint64)
+    exp = np.zeros((npoly, N), dtype=np.uint64)
+    for q in range(npoly):
+        pos = rng.choice(N, 6, replace=False)
+        pos[0] = 0 if q == 0 else pos[0]
+        val = rng.integers(-512, 512, 6)
+        a[q, pos] = val
+        exp[q] = _negacyclic_sparse(pos, val, b[q])
+    d_a = torch.from_numpy(a).to(cuda_device)
+    d_b = E.from_np_u64(b, cuda_device)
+    out = torch.empty((npoly, N), dtype=torch.int64, device=cuda_device)
+    _lib.call("fhe_debug_polymul", out.data_ptr(), d_a.data_ptr(), d_b.data_ptr(), npoly, N, k, level,
+              torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    err = (E.to_np_u64(out) - exp).view(np.int64)
+    bound = 2.0 ** 11 * 6 * 512 * 64
+    assert np.abs(err).max() <= bound, (C, np.abs(err).max(), bound)
+
+
+PBS_CASES = [
+    # p, n, k, N, level, base_log   (small n keeps the oracle fast; noise is negligible)
+    (2, 24, 1, 512, 2, 10),
+    (2, 16, 2, 256, 1, 20),
+    (3, 24, 3, 256, 2, 12),
+    (4, 40, 1, 2048, 1, 23),
+    (5, 24, 1, 4096, 2, 15),
+    (6, 20, 1, 8192, 2, 15),
+    (7, 12, 1, 16384, 2, 15),
+    (8, 12, 1, 32768, 2, 15),
+    (4, 16, 1, 8192, 3, 10),
+]
+
+
+@pytest.mark.parametrize("p_bits,n,k,N,level,base_log", PBS_CASES)
+def test_pbs_matches_oracle(oracle, cuda_device, p_bits, n, k, N, level, base_log):
+    p = E.CryptoParams(p=p_bits, n=n, k=k, N=N, pbs_level=level, pbs_base_log=base_log, ks_level=4,
+                       ks_base_log=4, lwe_std=2.0 ** -40, glwe_std=2.0 ** -55)
+    ks = E.KeySet(p, cuda_device, seed=5, keep_std_bsk=True)
+    ev = E.EvalKeys.of(ks)
+    rng = np.random.default_rng(p_bits)
+    B = 20
+    m = rng.integers(0, 1 << p_bits, B).astype(np.uint64)
+    tables = rng.integers(0, 1 << p_bits, (3, 1 << p_bits))
+    lut_idx = rng.integers(0, 3, B).astype(np.int32)
+    luts = E.build_lut_accumulators(p, tables)
+    for t in range(3):  # host LUT expansion == oracle's
+        assert np.array_equal(luts[t, k * N:], oracle.build_lut_poly(tables[t], p_bits, p_bits, N))
+    ct = E.encrypt(ks, m)
+    small = E.keyswitch(ev, ct)
+    d_luts = E.from_np_u64(luts, cuda_device)
+    d_idx = torch.from_numpy(lut_idx).to(cuda_device)
+    out = E.bootstrap(ev, small, d_luts, d_idx)
+    got = E.decrypt(ks, out)
+    exp = tables[lut_idx, m.astype(np.int64)].astype(np.uint64)
+    assert np.array_equal(got, exp)
+    # same inputs through the oracle's bootstrap (its own FFT): torus distance must be tiny
+    bsk_f = oracle.bsk_to_fourier(E.to_np_u64(ks.bsk_std))
+    ref = oracle.pbs(E.to_np_u64(small), bsk_f, luts, lut_idx, base_log)
+    diff = (E.to_np_u64(out) - ref).view(np.int64)
+    # tolerance: two fp64 FFT pipelines with different operation order; 2^-24 of the torus is far
+    # below the noise floor of any parameter set used (>= 2^-20 after a bootstrap)
+    assert np.abs(diff).max() < 2.0 ** 40, np.abs(diff).max()
+
+
+def test_linear_ops_bit_exact(oracle, cuda_device):
+    rng = np.random.default_rng(3)
+    L = 2049
+    a = rng.integers(0, 1 << 64, (37, L), dtype=np.uint64)
+    b = rng.integers(0, 1 << 64, (37, L), dtype=np.uint64)
+    da, db = E.from_np_u64(a, cuda_device), E.from_np_u64(b, cuda_device)
+    assert np.array_equal(E.to_np_u64(E.lin_add(da, db, L)), oracle.lin_add(a, b))
+    assert np.array_equal(E.to_np_u64(E.lin_sub(da, db, L)), oracle.lin_sub(a, b))
+    assert np.array_equal(E.to_np_u64(E.lin_neg(da, L)), oracle.lin_neg(a))
+    # broadcast through row maps
+    ia = torch.from_numpy(rng.integers(0, 37, 50).astype(np.int32)).to(cuda_device)
+    ib = torch.from_numpy(rng.integers(0, 37, 50).astype(np.int32)).to(cuda_device)
+    got = E.to_np_u64(E.lin_add(da, db, L, ia, ib, E=50))
+    assert np.array_equal(got, a[ia.cpu().numpy()] + b[ib.cpu().numpy()])
+    got = E.to_np_u64(E.lin_sub(da, db, L, ia, ib, E=50))
+    assert np.array_equal(got, a[ia.cpu().numpy()] - b[ib.cpu().numpy()])
+    pt = rng.integers(0, 1 << 64, 37, dtype=np.uint64)
+    dpt = E.from_np_u64(pt, cuda_device)
+    assert np.array_equal(E.to_np_u64(E.lin_add_plain(da, dpt, L)), oracle.lin_add_plain(a, pt))
+    exp = oracle.lin_neg(a)
+    exp[:, -1] += pt
+    assert np.array_equal(E.to_np_u64(E.lin_plain_sub(da, dpt, L)), exp)
+    c = rng.integers(-100, 100, 37).astype(np.int64)
+    dc = torch.from_numpy(c).to(cuda_device)
+    assert np.array_equal(E.to_np_u64(E.lin_mul_clear(da, dc, L)), oracle.lin_mul_clear(a, c))
+    # gather-mac (general linear map) incl. "no term" entries and bias
+    idx = rng.integers(-1, 37, (21, 9)).astype(np.int32)
+    w = rng.integers(-3, 4, (21, 9)).astype(np.int64)
+    bias = rng.integers(0, 1 << 64, 21, dtype=np.uint64)
+    got = E.lin_gather_mac(da, torch.from_numpy(idx).to(cuda_device), torch.from_numpy(w).to(cuda_device), L,
+                           E.from_np_u64(bias, cuda_device))
+    assert np.array_equal(E.to_np_u64(got), oracle.lin_gather_mac(a, idx, w, bias))
+    # dense matmul kernel == gather formulation
+    Mr, K, Nc = 5, 7, 19
+    x = rng.integers(0, 1 << 64, (Mr * K, L), dtype=np.uint64)
+    W = rng.integers(-4, 5, (K, Nc)).astype(np.int64)
+    gi = np.zeros((Mr * Nc, K), dtype=np.int32)
+    gw = np.zeros((Mr * Nc, K), dtype=np.int64)
+    for mm in range(Mr):
+        for nn in range(Nc):
+            gi[mm * Nc + nn] = mm * K + np.arange(K)
+            gw[mm * Nc + nn] = W[:, nn]
+    got = E.matmul_ct_clear(E.from_np_u64(x, cuda_device), torch.from_numpy(W).to(cuda_device), Mr, K, Nc, L)
+    assert np.array_equal(E.to_np_u64(got), oracle.lin_gather_mac(x, gi, gw))
