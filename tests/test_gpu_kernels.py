@@ -77,7 +77,7 @@ def _negacyclic_sparse(a_pos, a_val, b):
     out = np.zeros(N, dtype=np.uint64)
     for pos, val in zip(a_pos, a_val):
         rolled = np.concatenate([np.uint64(0) - b[N - pos:], b[:N - pos]]) if pos else b.copy()
-        out += rolled * np.uint64(val & 0xFFFFFFFFFFFFFFFF)
+        out += rolled * np.array(val, dtype=np.int64).view(np.uint64)
     return out
 
 
