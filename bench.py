@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the B200 encrypted-execution backend.
+
+    python bench.py --gpus N --steps K --warmup W            # this backend
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port, host cores)
+
+Metric (BASELINE.json): device-timed PBS/s.  Workload at N=1: BASELINE config 2 -- the 8-bit
+univariate `(x + 3) ** 2 // 5` on a 64x64 encrypted tensor (two chained table lookups = 8192
+keyswitch+bootstrap per step) with the published 8-bit parameter set (n=996, k=1, N=32768,
+pbs level 2 / base 2^15, ks level 7 / base 2^3).  A step = one `Server.run` of the circuit.
+
+  value : PBS/s with the input ciphertexts already resident in HBM (CUDA events, max over ranks)
+  e2e   : PBS/s through the public API (`Server.run`) with HOST ciphertext buffers: pinned host ->
+          device copy of the arguments and device -> host copy of the result inside the timed region
+  roofline : dominant kernel = k_pbs, fp64 (DFMA) bound; achieved = algorithmic flops per launch
+          (BASELINE.md section 4 formula) / mean k_pbs launch time (CUDA events on the launch stream);
+          peak = DFMA throughput measured live on this GPU (MEASURED_PEAKS.json has no fp64 figure)
+  cpu_baseline : the oracle (C port of the reference algorithm) on the box's host cores, on a
+          bounded sample of the same workload
+Multi-GPU: ciphertexts are independent -> each rank runs the circuit on its own 64x64 batch with
+replicated keys (deterministic keygen from one seed, no key broadcast, no data-path collective);
+weak scaling, value = all ranks' PBS / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "cfg2_univariate8_64x64"
+CPU_SAMPLE_PBS = 16
+
+
+def golden():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import load_golden
+
+    return load_golden(WORKLOAD)
+
+
+def flops_per_pbs(p):
+    M = p.N // 2
+    return p.n * ((p.k + 1) * (p.pbs_level + 1) * 5 * M * np.log2(M) + 8 * (p.k + 1) ** 2 * p.pbs_level * M)
+
+
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for line in self.lines:
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sample(params, n_pbs, native=True):
+    """Oracle timing on the host cores: keyswitch + bootstrap of `n_pbs` ciphertexts with synthetic
+    (bounded random) key material -- the run time of the port does not depend on key values."""
+    from oracle.oracle import Oracle
+
+    try:
+        o = Oracle(native=native)
+    except Exception:                                                     # noqa: BLE001
+        o = Oracle(native=False)
+    rng = np.random.default_rng(0)
+    p = params
+    chunk = rng.integers(0, 1 << 64, 1 << 16, dtype=np.uint64)
+    ksk = np.resize(chunk, (p.big_dim, p.ks_level, p.n + 1))
+    bsk_f = np.resize(rng.standard_normal(1 << 16) * 2.0 ** 40, (p.n, p.pbs_level, p.k + 1, p.k + 1, p.N // 2, 2))
+    ct = rng.integers(0, 1 << 64, (n_pbs, p.big_dim + 1), dtype=np.uint64)
+    lut = np.zeros((1, (p.k + 1) * p.N), dtype=np.uint64)
+    lut[0, p.k * p.N:] = o.build_lut_poly(np.arange(1 << p.p) % (1 << p.p), p.p, p.p, p.N)
+    t0 = time.perf_counter()
+    small = o.keyswitch(ct, ksk, p.ks_level, p.ks_base_log)
+    o.pbs(small, bsk_f, lut, None, p.pbs_base_log)
+    dt = time.perf_counter() - t0
+    return n_pbs / dt, dt
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference algorithm on all host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concrete_numpy_b200.params import REFERENCE_SETS
+
+    params = REFERENCE_SETS[8]
+    cores = os.cpu_count() or 1
+    n = max(CPU_SAMPLE_PBS, cores)
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_sample(params, min(n, cores))
+    times, count = [], 0
+    for _ in range(args.steps):
+        _, dt = cpu_sample(params, n)
+        times.append(dt)
+        count += n
+    total = sum(times)
+    value = count / total
+    line = {
+        "impl": "reference", "metric": "PBS/s (device-timed)", "value": value, "unit": "PBS/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "params": params.to_dict(), "sample": f"{n} PBS per step"},
+        "cpu_baseline": {"value": value, "unit": "PBS/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} keyswitch+bootstrap per step, synthetic BSK/KSK, oracle/tfhe_ref.c with OpenMP"},
+        "e2e": {"value": value, "unit": "PBS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from concrete_numpy_b200 import _lib, api, compiler as cc, engine as E
+    from concrete_numpy_b200.executor import Ct
+    from concrete_numpy_b200.params import REFERENCE_SETS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    doc = golden()
+    params = REFERENCE_SETS[8]
+    circuit = api.Circuit(doc["mlir"], doc["input_signs"], doc["output_signs"], api.Configuration(jit=True),
+                          crypto_parameters=params)
+    os.environ["CNP_B200_DEVICE"] = str(local)
+    keyset = cc.ClientSupport.key_set(circuit.server.client_specs.client_parameters, seed=42, device=dev)
+    circuit.client._keyset = keyset
+    ev = keyset.get_evaluation_keys()
+
+    rng = np.random.default_rng(rank)
+    x = rng.integers(0, 13, (64, 64))
+    enc = circuit.client.encrypt(x)                     # PublicArguments with a device Ct
+    ct_dev = enc.values[0]
+    host_in = torch.empty(ct_dev.data.shape, dtype=torch.int64, pin_memory=True)
+    host_in.copy_(ct_dev.data)
+    host_out = torch.empty(ct_dev.data.shape, dtype=torch.int64, pin_memory=True)
+    n_pbs_step = circuit.server._feedback.n_pbs
+    fp64_peak = E.measure_fp64_peak(dev)
+
+    # instrument the bootstrap launches with CUDA events (torch's current stream = launch stream)
+    pbs_events = []
+    raw_bootstrap = E.bootstrap
+
+    def timed_bootstrap(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = raw_bootstrap(*a, **k)
+        e1.record()
+        pbs_events.append((e0, e1, a[1].shape[0]))
+        return out
+
+    E.bootstrap = timed_bootstrap
+
+    def step_resident():
+        return circuit.server.run(enc, ev)
+
+    def step_e2e():
+        d = host_in.to(dev, non_blocking=True)
+        res = circuit.server.run(cc.PublicArguments([Ct(d, ct_dev.shape)]), ev)
+        host_out.copy_(res.values[0].data, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return res
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # correctness of what is being timed (decrypted result == reference clear evaluation)
+    res = step_resident()
+    got = circuit.client.decrypt(res)
+    correct = bool(np.array_equal(got, (x + 3) ** 2 // 5))
+    for _ in range(max(args.warmup - 1, 0)):
+        step_resident()
+    pbs_events.clear()
+    launches0 = _lib.launches_total()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launches_total() - launches0
+    pbs_ms = sum(a.elapsed_time(b) for a, b, _ in pbs_events)
+    pbs_cts = sum(n for _, _, n in pbs_events)
+    n_pbs_launch = len(pbs_events)
+
+    # end to end through Server.run with host buffers
+    step_e2e()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    g1.record()
+    barrier()
+    e2e_ms = g0.elapsed_time(g1)
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        ok = torch.tensor([1 if correct else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        correct = bool(ok.item())
+
+    if rank == 0:
+        total_pbs = n_pbs_step * args.steps * world
+        value = total_pbs / (ms * 1e-3)
+        e2e_value = total_pbs / (e2e_ms * 1e-3)
+        fl = flops_per_pbs(params)
+        achieved = pbs_cts * fl / (pbs_ms * 1e-3) / 1e12 if pbs_ms > 0 else 0.0
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n = max(CPU_SAMPLE_PBS, cores)
+            v, dt = cpu_sample(params, n)
+            cpu = {"value": v, "unit": "PBS/s", "cores": cores, "kind": "port",
+                   "sample": f"{n} keyswitch+bootstrap of the same parameter set in {dt:.1f} s, synthetic BSK/KSK, "
+                             "oracle/tfhe_ref.c (OpenMP over ciphertexts)"}
+        bytes_io = int(host_in.numel() * 8)
+        line = {
+            "metric": "PBS/s (device-timed)", "value": value, "unit": "PBS/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "circuit": "(x + 3) ** 2 // 5 on 64x64 eint<8>", "pbs_per_step_per_gpu": n_pbs_step,
+                       "params": params.to_dict(), "sharding": "by ciphertext, replicated BSK/KSK, no collective",
+                       "l2_flush": "inputs (1.07 GB of ciphertexts per step) exceed the 126 MB L2",
+                       "decrypted_output_correct": correct},
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "kernel": "k_pbs", "launches_timed": n_pbs_launch, "mean_launch_ms": pbs_ms / max(n_pbs_launch, 1),
+                         "flops_per_pbs": fl, "share_of_step": pbs_ms / ms if ms else None,
+                         "peak_source": "DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no fp64 entry)"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "PBS/s", "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

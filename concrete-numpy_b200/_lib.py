@@ -67,9 +67,17 @@ def load():
     return lib
 
 
+LAUNCH_COUNTS = {}   # entry point -> number of calls (each call launches >= 1 CUDA kernel)
+
+
+def launches_total() -> int:
+    return sum(LAUNCH_COUNTS.values())
+
+
 def call(name, *args):
     """Invoke a status-returning entry point and convert failures into FheError."""
     lib = load()
+    LAUNCH_COUNTS[name] = LAUNCH_COUNTS.get(name, 0) + 1
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise FheError(f"{name} failed with status {rc}: {lib.fhe_last_error().decode()}")

@@ -1,0 +1,487 @@
+"""
+Executor: walks the FHE / FHELinalg program parsed from the reference's MLIR text and launches
+the CUDA kernels through the C ABI (engine.py).  This is the body of `Server.run`
+(reference: concrete/numpy/compilation/server.py:270-286 -> `server_call`).
+
+Value model
+  * clear value      : numpy int64 array (shape from the MLIR type)
+  * encrypted value  : `Ct(data, shape)` with `data` a torch.int64 `[E, k*N+1]` device tensor,
+                       E = prod(shape), elements in row-major order
+
+Op semantics follow the reference's lowering, cited per handler
+(concrete/numpy/mlir/node_converter.py).  Linear / data-movement ops with numpy broadcasting are
+resolved ON THE HOST into int32 row maps once per program ("plans", cached), so each op is one
+kernel launch on device.
+"""
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import engine as E
+from .engine import CryptoParams, EvalKeys
+from .mlir_text.parser import Op, Program, TType
+
+
+@dataclass
+class Ct:
+    data: torch.Tensor            # [E, L] int64
+    shape: Tuple[int, ...]
+
+
+# ------------------------------------------------------------------- analysis -----
+
+@dataclass
+class ProgramInfo:
+    precision: int        # circuit-wide eint width p
+    n_pbs: int            # table lookups per run (keyswitch + bootstrap each)
+    tlu_depth: int
+    norm2: float          # largest squared 2-norm of the clear linear maps feeding a lookup / output
+    n_inputs_encrypted: int
+
+
+TLU_OPS = {"FHE.apply_lookup_table", "FHELinalg.apply_lookup_table", "FHELinalg.apply_mapped_lookup_table"}
+
+
+def analyze(program: Program) -> ProgramInfo:
+    """Static pass: precision, PBS count / depth and the noise growth of the linear parts."""
+    widths = {t.width for _, t in program.args if t.encrypted}
+    for op in program.ops:
+        if op.result_type is not None and op.result_type.encrypted:
+            widths.add(op.result_type.width)
+    if not widths:
+        raise RuntimeError("program has no encrypted value")
+    precision = max(widths)
+    nu: Dict[str, float] = {}      # variance multiplier (in units of a fresh/bootstrapped ct)
+    depth: Dict[str, int] = {}
+    const: Dict[str, np.ndarray] = {}
+    clear_bound: Dict[str, float] = {}
+    for name, t in program.args:
+        if t.encrypted:
+            nu[name], depth[name] = 1.0, 0
+        else:
+            clear_bound[name] = float(2 ** t.width)
+    n_pbs, worst = 0, 1.0
+
+    def cmax(name: str) -> float:
+        if name in const:
+            c = const[name]
+            return float(np.max(np.abs(c.astype(np.float64)))) if c.size else 0.0
+        return clear_bound.get(name, 1.0)
+
+    for op in program.ops:
+        r, o = op.result, op.operands
+        enc_in = [x for x in o if x in nu]
+        d = max([depth[x] for x in enc_in], default=0)
+        if op.name == "arith.constant":
+            const[r] = np.asarray(op.attrs["value"], dtype=np.int64)
+            continue
+        if op.name in TLU_OPS:
+            n_pbs += op.result_type.size
+            worst = max(worst, nu[o[0]])
+            nu[r], depth[r] = 1.0, d + 1
+            continue
+        base = op.name.split(".", 1)[1]
+        if base in ("add_eint", "sub_eint"):
+            v = nu[o[0]] + nu[o[1]]
+        elif base in ("add_eint_int", "sub_eint_int", "neg_eint"):
+            v = nu[o[0]]
+        elif base == "sub_int_eint":
+            v = nu[o[1]]
+        elif base == "mul_eint_int":
+            v = nu[o[0]] * cmax(o[1]) ** 2
+        elif base in ("zero", "zero_tensor"):
+            v = 0.0
+        elif base == "dot_eint_int":
+            c = const.get(o[1])
+            v = nu[o[0]] * (float(np.sum(c.astype(np.float64) ** 2)) if c is not None
+                            else cmax(o[1]) ** 2 * op.operand_types[0].size)
+        elif base in ("matmul_eint_int", "matmul_int_eint"):
+            ct_i, cl_i = (0, 1) if base == "matmul_eint_int" else (1, 0)
+            c = const.get(o[cl_i])
+            axis = -2 if base == "matmul_eint_int" else -1
+            if c is not None:
+                c2 = c.astype(np.float64) ** 2
+                s = float(np.max(c2.sum(axis=axis if c.ndim > 1 else 0))) if c.size else 0.0
+            else:
+                kdim = op.operand_types[cl_i].dims[axis if len(op.operand_types[cl_i].dims) > 1 else 0]
+                s = cmax(o[cl_i]) ** 2 * kdim
+            v = nu[o[ct_i]] * s
+        elif base == "conv2d":
+            c = const.get(o[1])
+            if c is not None:
+                s = float(np.max((c.astype(np.float64) ** 2).reshape(c.shape[0], -1).sum(axis=1)))
+            else:
+                wt = op.operand_types[1]
+                s = cmax(o[1]) ** 2 * (wt.size // wt.dims[0])
+            v = nu[o[0]] * s
+        elif base == "sum":
+            v = nu[o[0]] * max(op.operand_types[0].size // max(op.result_type.size, 1), 1)
+        elif base in ("concat", "from_elements", "insert_slice"):
+            v = max([nu[x] for x in enc_in], default=0.0)
+        else:   # transpose, tensor.* views
+            v = nu[enc_in[0]] if enc_in else 0.0
+        if op.result_type is not None and op.result_type.encrypted:
+            nu[r], depth[r] = v, d
+        elif r is not None and op.name.startswith("tensor."):
+            # clear tensors moved around: keep constants foldable for later bounds
+            clear_bound[r] = max([cmax(x) for x in o], default=1.0)
+    for name in program.returns:
+        if name in nu:
+            worst = max(worst, nu[name])
+    tlu_depth = max(depth.values(), default=0)
+    return ProgramInfo(precision, n_pbs, tlu_depth, worst, sum(1 for _, t in program.args if t.encrypted))
+
+
+# ------------------------------------------------------------------ helpers -------
+
+def _row_map(src_shape, dst_shape) -> Optional[np.ndarray]:
+    """int32 map dst element -> src element for numpy broadcasting (None = identity)."""
+    if tuple(src_shape) == tuple(dst_shape):
+        return None
+    n = int(np.prod(src_shape, dtype=np.int64)) if len(src_shape) else 1
+    idx = np.arange(n, dtype=np.int32).reshape(src_shape)
+    return np.ascontiguousarray(np.broadcast_to(idx, dst_shape)).reshape(-1)
+
+
+def _static_slices(offsets, sizes, strides):
+    out = []
+    for o, s, t in zip(offsets, sizes, strides):
+        stop = o + s * t
+        out.append(slice(o, stop if stop >= 0 else None, t))
+    return tuple(out)
+
+
+class Executor:
+    """Runs one parsed program on one device with one parameter set."""
+
+    def __init__(self, program: Program, params: CryptoParams, device):
+        self.program = program
+        self.params = params
+        self.device = torch.device(device)
+        self.L = params.ct_words
+        self._plans: Dict[int, dict] = {}          # per-op cached host plans + device uploads
+        self._consts: Dict[str, np.ndarray] = {}
+        for op in program.ops:
+            if op.name == "arith.constant":
+                self._consts[op.result] = np.asarray(op.attrs["value"], dtype=np.int64).reshape(op.result_type.dims)
+        self.handlers: Dict[str, Callable] = {
+            "add_eint": self._add_eint, "sub_eint": self._sub_eint,
+            "add_eint_int": self._add_eint_int, "sub_eint_int": self._sub_eint_int,
+            "sub_int_eint": self._sub_int_eint, "neg_eint": self._neg_eint,
+            "mul_eint_int": self._mul_eint_int,
+            "apply_lookup_table": self._tlu, "apply_mapped_lookup_table": self._tlu,
+            "zero": self._zero, "zero_tensor": self._zero,
+            "dot_eint_int": self._dot, "matmul_eint_int": self._matmul, "matmul_int_eint": self._matmul,
+            "conv2d": self._conv2d, "sum": self._sum, "concat": self._concat, "transpose": self._transpose,
+            "extract": self._extract, "extract_slice": self._extract_slice, "insert_slice": self._insert_slice,
+            "collapse_shape": self._reshape, "expand_shape": self._reshape, "from_elements": self._from_elements,
+        }
+        self.last_stats = {}
+
+    # -- device upload helpers (cached per op)
+    def _dev(self, arr: Optional[np.ndarray], dtype=None) -> Optional[torch.Tensor]:
+        if arr is None:
+            return None
+        a = np.array(arr if dtype is None else arr.astype(dtype), copy=True, order="C")
+        return torch.from_numpy(a).to(self.device)
+
+    def _plan(self, op: Op, build: Callable[[], dict]) -> dict:
+        key = id(op)
+        if key not in self._plans:
+            self._plans[key] = build()
+        return self._plans[key]
+
+    def _encode(self, c: np.ndarray) -> np.ndarray:
+        """clear ints -> plaintexts: (c mod 2^(p+1)) << (63 - p), as int64 bit patterns."""
+        p = self.params.p
+        v = (np.asarray(c, dtype=np.int64).astype(np.uint64) & np.uint64((1 << (p + 1)) - 1)) << np.uint64(63 - p)
+        return v.view(np.int64)
+
+    # ---------------------------------------------------------------- run ---------
+    def run(self, ev: EvalKeys, args: List) -> List:
+        """args: one entry per function argument (Ct for encrypted, numpy array / int for clear)."""
+        env: Dict[str, object] = {}
+        for (name, t), a in zip(self.program.args, args):
+            if t.encrypted:
+                if not isinstance(a, Ct):
+                    raise RuntimeError(f"argument {name} must be encrypted")
+                if tuple(a.shape) != t.dims:
+                    raise RuntimeError(f"argument {name}: shape {a.shape} != {t.dims}")
+                env[name] = a
+            else:
+                env[name] = np.asarray(a, dtype=np.int64).reshape(t.dims)
+        env.update(self._consts)
+        self._ev = ev
+        n_pbs = 0
+        for op in self.program.ops:
+            if op.name == "arith.constant":
+                continue
+            base = op.name.split(".", 1)[1]
+            h = self.handlers.get(base)
+            if h is None:
+                raise RuntimeError(f"operation {op.name} is not supported by the B200 backend")
+            env[op.result] = h(op, [env[x] for x in op.operands])
+            if base in ("apply_lookup_table", "apply_mapped_lookup_table"):
+                n_pbs += op.result_type.size
+        self.last_stats = {"n_pbs": n_pbs}
+        return [env[r] for r in self.program.returns]
+
+    # ------------------------------------------------------------- elementwise ----
+    def _binary_ct(self, op: Op, a: Ct, b: Ct, fn) -> Ct:
+        shape = op.result_type.dims
+        plan = self._plan(op, lambda: {"ia": self._dev(_row_map(a.shape, shape)), "ib": self._dev(_row_map(b.shape, shape))})
+        n = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        return Ct(fn(a.data, b.data, self.L, plan["ia"], plan["ib"], n), shape)
+
+    def _add_eint(self, op, v):          # node_converter.py:216-242
+        return self._binary_ct(op, v[0], v[1], E.lin_add)
+
+    def _sub_eint(self, op, v):          # node_converter.py:1062-1092
+        return self._binary_ct(op, v[0], v[1], E.lin_sub)
+
+    def _clear_operand(self, op: Op, c, shape, encode: bool, negate: bool = False):
+        """Broadcast a clear operand to the result shape (encoded as plaintexts when `encode`);
+        compile-time constants are uploaded once per program."""
+        cname = [x for x, t in zip(op.operands, op.operand_types) if not t.encrypted][0]
+
+        def build():
+            cc = np.broadcast_to(np.asarray(c, dtype=np.int64), shape).reshape(-1)
+            cc = -cc if negate else cc
+            return self._dev(self._encode(cc) if encode else np.ascontiguousarray(cc))
+
+        if cname not in self._consts:
+            return build()
+        key = ("clear", id(op))
+        if key not in self._plans:
+            self._plans[key] = build()
+        return self._plans[key]
+
+    def _ct_map(self, op: Op, a: Ct, shape):
+        key = ("ia", id(op))
+        if key not in self._plans:
+            self._plans[key] = self._dev(_row_map(a.shape, shape))
+        return self._plans[key]
+
+    def _add_eint_int(self, op, v):      # ct + clear: plaintext added to the body only
+        shape = op.result_type.dims
+        pt = self._clear_operand(op, v[1], shape, encode=True)
+        return Ct(E.lin_add_plain(v[0].data, pt, self.L, self._ct_map(op, v[0], shape)), shape)
+
+    def _sub_eint_int(self, op, v):      # ct - clear
+        shape = op.result_type.dims
+        pt = self._clear_operand(op, v[1], shape, encode=True, negate=True)
+        return Ct(E.lin_add_plain(v[0].data, pt, self.L, self._ct_map(op, v[0], shape)), shape)
+
+    def _sub_int_eint(self, op, v):      # clear - ct
+        shape = op.result_type.dims
+        pt = self._clear_operand(op, v[0], shape, encode=True)
+        return Ct(E.lin_plain_sub(v[1].data, pt, self.L, self._ct_map(op, v[1], shape)), shape)
+
+    def _neg_eint(self, op, v):          # node_converter.py:652-669
+        return Ct(E.lin_neg(v[0].data, self.L), v[0].shape)
+
+    def _mul_eint_int(self, op, v):      # ct * clear int (all words), node_converter.py:630-650
+        shape = op.result_type.dims
+        c = self._clear_operand(op, v[1], shape, encode=False)
+        return Ct(E.lin_mul_clear(v[0].data, c, self.L, self._ct_map(op, v[0], shape)), shape)
+
+    def _zero(self, op, v):              # trivial encryption of 0: all-zero LWE (node_converter.py:1232-1248)
+        shape = op.result_type.dims
+        n = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        return Ct(torch.zeros((n, self.L), dtype=torch.int64, device=self.device), shape)
+
+    # --------------------------------------------------------------- lookups ------
+    def _tlu(self, op, v):               # keyswitch + PBS per element (node_converter.py:1129-1208)
+        x: Ct = v[0]
+        p = self.params
+
+        def build():
+            luts = np.asarray(v[1], dtype=np.int64)
+            if luts.ndim == 1:
+                luts = luts[None, :]
+            if luts.shape[1] != (1 << p.p):
+                raise RuntimeError(f"lookup table of {luts.shape[1]} entries on {p.p}-bit ciphertexts")
+            acc = E.build_lut_accumulators(p, luts)
+            idx = None
+            if op.name.endswith("apply_mapped_lookup_table"):
+                m = np.broadcast_to(np.asarray(v[2], dtype=np.int64), x.shape).reshape(-1)
+                idx = self._dev(m.astype(np.int32))
+            return {"luts": E.from_np_u64(acc, self.device), "idx": idx}
+
+        plan = self._plan(op, build)
+        out = E.table_lookup(self._ev, x.data, plan["luts"], plan["idx"])
+        return Ct(out, op.result_type.dims)
+
+    # ---------------------------------------------------- clear-weighted linear ---
+    def _gather(self, op: Op, x: Ct, build: Callable[[], Tuple[np.ndarray, np.ndarray, Optional[np.ndarray]]]) -> Ct:
+        def mk():
+            idx, w, bias = build()
+            return {"idx": self._dev(idx.astype(np.int32)), "w": self._dev(w.astype(np.int64)),
+                    "bias": None if bias is None else self._dev(self._encode(bias))}
+
+        clear_names = [n for n, t in zip(op.operands, op.operand_types) if not t.encrypted]
+        if all(n in self._consts for n in clear_names):
+            plan = self._plan(op, mk)
+        else:
+            plan = mk()
+        out = E.lin_gather_mac(x.data, plan["idx"], plan["w"], self.L, plan["bias"])
+        return Ct(out, op.result_type.dims)
+
+    def _dot(self, op, v):               # node_converter.py:497-524 (vector . vector)
+        x, c = v
+        return self._gather(op, x, lambda: (np.arange(x.data.shape[0])[None, :], np.asarray(c).reshape(1, -1), None))
+
+    def _matmul(self, op, v):            # node_converter.py:596-616, numpy matmul broadcasting
+        eint_left = op.name.endswith("matmul_eint_int")
+        x: Ct = v[0] if eint_left else v[1]
+        W = np.asarray(v[1] if eint_left else v[0], dtype=np.int64)
+        out_shape = op.result_type.dims
+        if eint_left and len(x.shape) == 2 and W.ndim == 2 and W.shape[0] * 16 * 8 <= 48 * 1024:
+            Mr, K = x.shape
+            wname = op.operands[1]
+            if wname in self._consts:
+                Wd = self._plan(op, lambda: {"W": self._dev(W)})["W"]
+            else:
+                Wd = self._dev(W)
+            return Ct(E.matmul_ct_clear(x.data, Wd, Mr, K, W.shape[1], self.L), out_shape)
+
+        def build():
+            xi = np.arange(x.data.shape[0], dtype=np.int64).reshape(x.shape)
+            a, b = (xi, W) if eint_left else (W, xi)
+            a2 = a[None, :] if a.ndim == 1 else a
+            b2 = b[:, None] if b.ndim == 1 else b
+            Mr, K, Nc = a2.shape[-2], a2.shape[-1], b2.shape[-1]
+            batch = np.broadcast_shapes(a2.shape[:-2], b2.shape[:-2])
+            A = np.broadcast_to(a2, batch + (Mr, K))[..., :, None, :]            # [.., M, 1, K]
+            Bm = np.swapaxes(np.broadcast_to(b2, batch + (K, Nc)), -1, -2)[..., None, :, :]  # [.., 1, N, K]
+            full = batch + (Mr, Nc, K)
+            A, Bm = np.broadcast_to(A, full), np.broadcast_to(Bm, full)
+            idx, w = (A, Bm) if eint_left else (Bm, A)
+            return idx.reshape(-1, K), w.reshape(-1, K), None
+
+        return self._gather(op, x, build)
+
+    def _conv2d(self, op, v):            # node_converter.py:436-483; semantics concrete/onnx/convolution.py:433-520
+        x: Ct = v[0]
+        W = np.asarray(v[1], dtype=np.int64)
+        bias = np.asarray(v[2], dtype=np.int64) if len(v) == 3 else None
+        a = op.attrs
+        pads = [int(t) for t in np.asarray(a["padding"][0] if isinstance(a.get("padding"), tuple) else a.get("padding", [0, 0, 0, 0])).reshape(-1)]
+        strides = [int(t) for t in np.asarray(a["strides"][0] if isinstance(a.get("strides"), tuple) else a.get("strides", [1, 1])).reshape(-1)]
+        dil = [int(t) for t in np.asarray(a["dilations"][0] if isinstance(a.get("dilations"), tuple) else a.get("dilations", [1, 1])).reshape(-1)]
+        group = int(a.get("group", 1))
+        out_shape = op.result_type.dims
+
+        def build():
+            Nb, Cin, H, Wd = x.shape
+            F, Cg, KH, KW = W.shape
+            _, _, OH, OW = out_shape
+            xi = np.arange(x.data.shape[0], dtype=np.int64).reshape(x.shape)
+            K = Cg * KH * KW
+            idx = np.full((Nb, F, OH, OW, K), -1, dtype=np.int64)
+            w = np.zeros((Nb, F, OH, OW, K), dtype=np.int64)
+            fpg = F // group
+            oh = np.arange(OH)[:, None]
+            ow = np.arange(OW)[None, :]
+            for f in range(F):
+                g = f // fpg
+                for c in range(Cg):
+                    for kh in range(KH):
+                        for kw in range(KW):
+                            kk = (c * KH + kh) * KW + kw
+                            ih = oh * strides[0] - pads[0] + kh * dil[0]
+                            iw = ow * strides[1] - pads[1] + kw * dil[1]
+                            ok = (ih >= 0) & (ih < H) & (iw >= 0) & (iw < Wd)
+                            ihc, iwc = np.clip(ih, 0, H - 1), np.clip(iw, 0, Wd - 1)
+                            src = xi[:, g * Cg + c][:, ihc, iwc]                 # [Nb, OH, OW]
+                            idx[:, f, :, :, kk] = np.where(ok[None], src, -1)
+                            w[:, f, :, :, kk] = W[f, c, kh, kw]
+            b = None
+            if bias is not None:
+                b = np.broadcast_to(bias.reshape(1, F, 1, 1), out_shape).reshape(-1)
+            return idx.reshape(-1, K), w.reshape(-1, K), b
+
+        return self._gather(op, x, build)
+
+    def _sum(self, op, v):               # node_converter.py:1094-1127
+        x: Ct = v[0]
+        axes = [int(t) for t in op.attrs.get("axes", [])]
+        keep = bool(op.attrs.get("keep_dims", False))
+        out_shape = op.result_type.dims
+
+        def build():
+            xi = np.arange(x.data.shape[0], dtype=np.int64).reshape(x.shape)
+            ax = tuple(axes) if axes else tuple(range(len(x.shape)))
+            moved = np.moveaxis(xi, ax, tuple(range(len(x.shape) - len(ax), len(x.shape))))
+            K = int(np.prod([x.shape[t] for t in ax], dtype=np.int64)) if ax else 1
+            idx = moved.reshape(-1, K)
+            return idx, np.ones_like(idx), None
+
+        out = self._gather(op, x, build)
+        _ = keep
+        return Ct(out.data, out_shape)
+
+    # ------------------------------------------------------------ data movement ---
+    def _gather_rows(self, op: Op, srcs: List[Ct], build_index: Callable[[], np.ndarray], shape) -> Ct:
+        """out rows = concat(srcs) rows picked by an index map computed with numpy on the host."""
+        plan = self._plan(op, lambda: {"idx": self._dev(build_index().reshape(-1).astype(np.int64))})
+        data = srcs[0].data if len(srcs) == 1 else torch.cat([s.data for s in srcs], dim=0)
+        return Ct(torch.index_select(data, 0, plan["idx"]), shape)
+
+    @staticmethod
+    def _ids(cts: List[Ct]) -> List[np.ndarray]:
+        out, base = [], 0
+        for c in cts:
+            n = c.data.shape[0]
+            out.append(np.arange(base, base + n, dtype=np.int64).reshape(c.shape))
+            base += n
+        return out
+
+    def _clear_or_ct(self, op, vals, fn):
+        """Apply a pure data-movement numpy function either on clear arrays or on row ids."""
+        if all(not isinstance(t, Ct) for t in vals):
+            return fn([np.asarray(t) for t in vals])
+        cts = [t for t in vals if isinstance(t, Ct)]
+        if len(cts) != len(vals):
+            raise RuntimeError(f"{op.name}: mixing clear and encrypted operands is not supported")
+        return self._gather_rows(op, cts, lambda: fn(self._ids(cts)), op.result_type.dims)
+
+    def _concat(self, op, v):            # node_converter.py:341-394
+        axis = int(op.attrs.get("axis", 0))
+        return self._clear_or_ct(op, v, lambda a: np.concatenate(a, axis=axis))
+
+    def _transpose(self, op, v):         # node_converter.py:1210-1230 (empty axes = reverse)
+        axes = [int(t) for t in op.attrs.get("axes", [])]
+        return self._clear_or_ct(op, v[:1], lambda a: np.transpose(a[0], axes if axes else None))
+
+    def _reshape(self, op, v):           # tensor.collapse_shape / expand_shape (node_converter.py:725-842)
+        shape = op.result_type.dims
+        if isinstance(v[0], Ct):
+            return Ct(v[0].data, shape)
+        return np.asarray(v[0]).reshape(shape)
+
+    def _extract(self, op, v):           # tensor.extract with constant indices (node_converter.py:917-1039)
+        index = tuple(int(np.asarray(t)) for t in v[1:])
+        return self._clear_or_ct(op, v[:1], lambda a: a[0][index])
+
+    def _extract_slice(self, op, v):
+        sl = _static_slices(op.attrs["offsets"], op.attrs["sizes"], op.attrs["strides"])
+        shape = op.result_type.dims
+        return self._clear_or_ct(op, v[:1], lambda a: a[0][sl].reshape(shape))
+
+    def _insert_slice(self, op, v):      # tensor.insert_slice (assign.static, node_converter.py:855-915)
+        sl = _static_slices(op.attrs["offsets"], op.attrs["sizes"], op.attrs["strides"])
+
+        def fn(a):
+            out = a[1].copy()
+            out[sl] = a[0].reshape(out[sl].shape)
+            return out
+
+        return self._clear_or_ct(op, v, fn)
+
+    def _from_elements(self, op, v):     # tensor.from_elements (node_converter.py:266-306)
+        shape = op.result_type.dims
+        return self._clear_or_ct(op, v, lambda a: np.stack([t.reshape(()) for t in a]).reshape(shape))

@@ -1,0 +1,192 @@
+"""
+Crypto-parameter selection for one circuit: stands in for `concrete-optimizer` (inside the absent
+concrete-compiler wheel), which the reference drives through
+`CompilationOptions.set_p_error / set_global_p_error` (concrete/numpy/compilation/server.py:102-126).
+
+Given the circuit-wide precision `p` (the reference forces ONE width on every encrypted value,
+concrete/numpy/mlir/graph_converter.py:315-322), the largest squared 2-norm of the clear linear
+maps feeding a table lookup, and the per-lookup error budget, search (n, k, N, pbs level/base,
+ks level/base) minimising an fp64/int cost model subject to
+
+    erfc( 2^-(p+2) / (sqrt(2) * sigma_total) ) <= p_error
+    sigma_total^2 = norm2 * V_pbs_out + V_keyswitch + V_modswitch
+
+with the variance formulas below (torus units, binary keys) and 128-bit security curves
+(noise std as a function of LWE dimension) fitted to the published TFHE-rs `PARAM_MESSAGE_x_CARRY_y`
+sets, which were produced by the same concrete-optimizer.
+
+The formulas are validated empirically on device by tests/test_noise.py.
+"""
+
+import math
+from functools import lru_cache
+
+import numpy as np
+
+from .engine import CryptoParams
+
+SECURITY_SLOPE = -0.0264
+SECURITY_BIAS = 2.48
+MIN_LOG2_STD = -62.0          # ~2.17e-19, the floor used for 64-bit torus
+SMEM_MAX = 232448             # must match PBS_SMEM_MAX in csrc/pbs.cu
+
+
+def secure_log2_std(dim: int) -> float:
+    """log2 of the minimal noise std (relative to q) giving 128-bit security at LWE dimension `dim`."""
+    return max(SECURITY_SLOPE * dim + SECURITY_BIAS, MIN_LOG2_STD)
+
+
+def pbs_cluster_size(N: int, k: int, level: int) -> int:
+    """Mirror of choose_cluster() in csrc/pbs.cu (CTAs per ciphertext)."""
+    M = N // 2
+    C = 1
+    while C <= 8:
+        if M // C < 64 or M // (C * C) < 1:
+            break
+        smem = (k + 1) * (N // C) * 8 + (k + 1) * level * (M // C) * 16
+        if smem <= SMEM_MAX:
+            return C
+        C *= 2
+    return -1
+
+
+# ---------------------------------------------------------------- noise model ----
+
+def variance_pbs_out(n, k, N, level, base_log, glwe_var):
+    """Output variance of a programmable bootstrap (blind rotation of n CMUXes)."""
+    B2 = 4.0 ** base_log
+    ext = level * (k + 1) * N * (B2 + 2.0) / 12.0 * glwe_var
+    rounding = (1.0 + k * N / 2.0) / (12.0 * 4.0 ** (base_log * level))
+    fft = level * (k + 1) * N * B2 * math.log2(N) * 2.0 ** -108
+    return n * (ext + rounding + fft)
+
+
+def variance_keyswitch(kN, level, base_log, lwe_var):
+    B2 = 4.0 ** base_log
+    return kN * level * (B2 + 2.0) / 12.0 * lwe_var + kN / 2.0 / (12.0 * 4.0 ** (base_log * level))
+
+
+def variance_modswitch(n, N):
+    return (1.0 / 12.0 + n / 24.0) / (4.0 * N * N)
+
+
+def p_error_of(p, variance):
+    """Probability that noise of the given variance leaves the half-box 2^-(p+2)."""
+    if variance <= 0:
+        return 0.0
+    z = 2.0 ** -(p + 2) / math.sqrt(2.0 * variance)
+    return math.erfc(z)
+
+
+def input_variance(params: CryptoParams, norm2: float) -> float:
+    """Variance at the input of a table lookup (after clear linear maps of squared 2-norm norm2)."""
+    v_out = variance_pbs_out(params.n, params.k, params.N, params.pbs_level, params.pbs_base_log,
+                             params.glwe_std ** 2)
+    v_in = max(v_out, params.glwe_std ** 2) * max(norm2, 1.0)
+    return (v_in + variance_keyswitch(params.big_dim, params.ks_level, params.ks_base_log, params.lwe_std ** 2)
+            + variance_modswitch(params.n, params.N))
+
+
+def estimate_p_error(params: CryptoParams, norm2: float) -> float:
+    return p_error_of(params.p, input_variance(params, norm2))
+
+
+# ---------------------------------------------------------------- cost model -----
+
+def pbs_flops(n, k, N, level):
+    """Real flops of one bootstrap (BASELINE.md section 4 / SURVEY 8d)."""
+    M = N / 2
+    return n * ((k + 1) * (level + 1) * 5 * M * math.log2(M) + 8 * (k + 1) ** 2 * level * M)
+
+
+def ks_macs(kN, n, level):
+    return kN * level * (n + 1)
+
+
+KS_MAC_COST = 7.0   # one u64 MAC on the int pipe costs about this many fp64 flops of device time
+
+
+@lru_cache(maxsize=None)
+def select_parameters(p: int, norm2: float = 1.0, p_error: float = 1e-9) -> CryptoParams:
+    """Cheapest parameter set meeting `p_error` per table lookup at precision p."""
+    if p < 1 or p > 8:
+        raise ValueError(
+            f"precision {p} bits is outside the native PBS range 1..8 of this backend "
+            "(the reference would switch to CRT / WoP-PBS; see DESIGN.md 'out of scope')"
+        )
+    target_z = _z_for_p_error(p_error)
+    max_var = (2.0 ** -(p + 2) / target_z) ** 2        # erfc(z/sqrt2) <= p_error  <=> sigma <= delta/z
+    best = None
+    shapes = [(3, 512), (2, 1024), (1, 2048), (1, 4096), (1, 8192), (1, 16384), (1, 32768)]
+    n_grid = np.arange(450, 1201, 2)
+    lwe_var_grid = 4.0 ** np.maximum(SECURITY_SLOPE * n_grid + SECURITY_BIAS, MIN_LOG2_STD)
+    for k, N in shapes:
+        if N < (1 << (p + 1)):
+            continue
+        glwe_var = 4.0 ** secure_log2_std(k * N)
+        v_ms = (1.0 / 12.0 + n_grid / 24.0) / (4.0 * N * N)
+        for level in (1, 2, 3):
+            if pbs_cluster_size(N, k, level) < 0:
+                continue
+            for base_log in range(4, 36):
+                if level * base_log > 52:
+                    break
+                v_out_per_n = variance_pbs_out(1, k, N, level, base_log, glwe_var)
+                v_in = np.maximum(v_out_per_n * n_grid, glwe_var) * max(norm2, 1.0)
+                budget = max_var - v_in - v_ms                     # what is left for the keyswitch
+                if not np.any(budget > 0):
+                    continue
+                pbs_cost = np.array([pbs_flops(int(n), k, N, level) for n in (n_grid[0], n_grid[-1])])
+                pbs_cost = pbs_cost[0] + (pbs_cost[1] - pbs_cost[0]) * (n_grid - n_grid[0]) / (n_grid[-1] - n_grid[0])
+                for ks_level in range(1, 10):
+                    for ks_base_log in range(1, 12):
+                        if ks_level * ks_base_log > 40:
+                            break
+                        B2 = 4.0 ** ks_base_log
+                        v_ks = (k * N * ks_level * (B2 + 2.0) / 12.0 * lwe_var_grid
+                                + k * N / 24.0 / 4.0 ** (ks_base_log * ks_level))
+                        ok = v_ks <= budget
+                        if not np.any(ok):
+                            continue
+                        cost = pbs_cost + KS_MAC_COST * k * N * ks_level * (n_grid + 1)
+                        cost = np.where(ok, cost, np.inf)
+                        j = int(np.argmin(cost))
+                        if best is None or cost[j] < best[0]:
+                            best = (float(cost[j]), int(n_grid[j]), k, N, level, base_log, ks_level, ks_base_log)
+    if best is None:
+        raise ValueError(f"no parameter set reaches p_error={p_error:g} at {p} bits with 2-norm^2={norm2:g}")
+    _, n, k, N, level, base_log, ks_level, ks_base_log = best
+    return CryptoParams(p=p, n=n, k=k, N=N, pbs_level=level, pbs_base_log=base_log, ks_level=ks_level,
+                        ks_base_log=ks_base_log, lwe_std=2.0 ** secure_log2_std(n),
+                        glwe_std=2.0 ** secure_log2_std(k * N))
+
+
+def _z_for_p_error(p_error: float) -> float:
+    """z such that erfc(z / sqrt(2)) == p_error (bisection; p_error in (0, 1))."""
+    p_error = min(max(p_error, 1e-300), 0.999999)
+    lo, hi = 0.0, 40.0
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        if math.erfc(mid / math.sqrt(2.0)) > p_error:
+            lo = mid
+        else:
+            hi = mid
+    return hi
+
+
+def complexity(params: CryptoParams, n_pbs: int) -> float:
+    """CompilationFeedback.complexity stand-in: modelled fp64-equivalent operations of a run."""
+    return float(n_pbs) * (pbs_flops(params.n, params.k, params.N, params.pbs_level)
+                           + KS_MAC_COST * ks_macs(params.big_dim, params.n, params.ks_level))
+
+
+# Published TFHE-rs sets the curves were fitted to (provenance only; used by tests and the bench
+# so that numbers are comparable with other TFHE implementations).
+REFERENCE_SETS = {
+    4: CryptoParams(p=4, n=742, k=1, N=2048, pbs_level=1, pbs_base_log=23, ks_level=5, ks_base_log=3,
+                    lwe_std=7.069849454709433e-06, glwe_std=2.9403601535432533e-16),
+    6: CryptoParams(p=6, n=864, k=1, N=8192, pbs_level=2, pbs_base_log=15, ks_level=6, ks_base_log=3,
+                    lwe_std=7.57998020150446e-07, glwe_std=2.168404344971009e-19),
+    8: CryptoParams(p=8, n=996, k=1, N=32768, pbs_level=2, pbs_base_log=15, ks_level=7, ks_base_log=3,
+                    lwe_std=6.767666038309478e-08, glwe_std=2.168404344971009e-19),
+}

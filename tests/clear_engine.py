@@ -1,0 +1,101 @@
+"""
+Clear stand-in for concrete_numpy_b200.engine used by the CPU tests of the host logic
+(parser + executor plans + encodings): a "ciphertext" is a single torus word (LWE of dimension 0,
+ct_words = 1) holding `m << (63 - p)`, so every linear op of the executor runs the same wrapping
+u64 formulas as the CUDA kernels and a table lookup is decode -> (negacyclic) table -> encode.
+TEST INFRASTRUCTURE ONLY; never imported by the product.
+"""
+import numpy as np
+import torch
+
+
+def _u(t):
+    return t.detach().cpu().numpy().view(np.uint64)
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64))
+
+
+def from_np_u64(a, device):
+    return _t(np.ascontiguousarray(a, dtype=np.uint64))
+
+
+def build_lut_accumulators(params, tables):
+    return np.asarray(tables).astype(np.int64).view(np.uint64)
+
+
+def _rows(x, idx):
+    return x if idx is None else x[idx.numpy()]
+
+
+def lin_add(a, b, L, ia=None, ib=None, E=None):
+    return _t(_rows(_u(a), ia) + _rows(_u(b), ib))
+
+
+def lin_sub(a, b, L, ia=None, ib=None, E=None):
+    return _t(_rows(_u(a), ia) - _rows(_u(b), ib))
+
+
+def lin_neg(a, L, ia=None, E=None):
+    return _t(np.uint64(0) - _rows(_u(a), ia))
+
+
+def lin_add_plain(a, pt, L, ia=None):
+    out = _rows(_u(a), ia).copy()
+    out[:, -1] += _u(pt)
+    return _t(out)
+
+
+def lin_plain_sub(a, pt, L, ia=None):
+    out = np.uint64(0) - _rows(_u(a), ia)
+    out[:, -1] += _u(pt)
+    return _t(out)
+
+
+def lin_mul_clear(a, c, L, ia=None):
+    return _t(_rows(_u(a), ia) * c.numpy().view(np.uint64)[:, None])
+
+
+def lin_gather_mac(x, idx, w, L, bias=None):
+    xu = _u(x)
+    idx, w = idx.numpy(), w.numpy().view(np.uint64)
+    out = np.zeros((idx.shape[0], xu.shape[1]), dtype=np.uint64)
+    for j in range(idx.shape[1]):
+        ok = idx[:, j] >= 0
+        out[ok] += w[ok, j][:, None] * xu[idx[ok, j]]
+    if bias is not None:
+        out[:, -1] += _u(bias)
+    return _t(out)
+
+
+def matmul_ct_clear(x, W, Mr, K, Nc, L):
+    xu = _u(x).reshape(Mr, K, L)
+    Wu = W.numpy().view(np.uint64)
+    out = np.zeros((Mr, Nc, L), dtype=np.uint64)
+    for kk in range(K):
+        out += Wu[kk][None, :, None] * xu[:, kk][:, None, :]
+    return _t(out.reshape(Mr * Nc, L))
+
+
+class ClearEval:
+    """What executor.py receives as `ev`; carries the precision for table lookups."""
+
+    def __init__(self, params):
+        self.params = params
+
+
+def decode(body_u64, p):
+    t = body_u64 >> np.uint64(64 - p - 2)
+    return ((t >> np.uint64(1)) + (t & np.uint64(1))) & np.uint64((1 << (p + 1)) - 1)
+
+
+def table_lookup(ev, ct, luts, lut_idx=None):
+    p = ev.params.p
+    m = decode(_u(ct)[:, -1], p).astype(np.int64)
+    tables = _u(luts)
+    which = np.zeros(m.size, dtype=np.int64) if lut_idx is None else lut_idx.numpy().astype(np.int64)
+    neg = m >= (1 << p)                       # padding bit set: the bootstrap is negacyclic
+    val = tables[which, np.where(neg, m - (1 << p), m)]
+    val = np.where(neg, np.uint64(0) - val, val)
+    return _t((val << np.uint64(63 - p))[:, None])
