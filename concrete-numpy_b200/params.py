@@ -57,7 +57,10 @@ def variance_pbs_out(n, k, N, level, base_log, glwe_var):
     B2 = 4.0 ** base_log
     ext = level * (k + 1) * N * (B2 + 2.0) / 12.0 * glwe_var
     rounding = (1.0 + k * N / 2.0) / (12.0 * 4.0 ** (base_log * level))
-    fft = level * (k + 1) * N * B2 * math.log2(N) * 2.0 ** -108
+    # fp64 FFT precision loss of one external product (53-bit mantissa on a 64-bit torus): the
+    # empirical law published with concrete-optimizer, 2^-2.577 * 2^22 * l * B^2 * N^2 * (k+1) / 2^128;
+    # measured on device by scripts/noise_probe.py (within 1 bit, on the conservative side)
+    fft = level * (k + 1) * B2 * float(N) ** 2 * 2.0 ** (-2.577 + 22 - 128)
     return n * (ext + rounding + fft)
 
 

@@ -1,0 +1,69 @@
+"""Noise parity of the programmable bootstrap (floating point path): tolerance from
+BASELINE.json north_star -- output noise VARIANCE <= 2x the oracle's on the same inputs, and the
+empirical error rate at or below the p_error the parameters were selected for.  Also pins the
+variance model of params.py (keyswitch within 0.5 bit, bootstrap within 1.5 bits of std)."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from concrete_numpy_b200 import engine as E
+from concrete_numpy_b200 import params as P
+
+
+def _log2_std(err_u64):
+    return math.log2(err_u64.view(np.int64).astype(np.float64).std() / 2.0 ** 64 + 1e-300)
+
+
+@pytest.mark.parametrize("bits,B,oracle_n", [(4, 2048, 256), (6, 256, 8)])
+def test_bootstrap_noise_vs_oracle_and_model(oracle, cuda_device, bits, B, oracle_n):
+    p = P.REFERENCE_SETS[bits]
+    ks = E.KeySet(p, cuda_device, seed=3, keep_std_bsk=True)
+    ev = E.EvalKeys.of(ks)
+    rng = np.random.default_rng(1)
+    m = rng.integers(0, 1 << p.p, B).astype(np.uint64)
+    pt = m << np.uint64(63 - p.p)
+    ct = E.encrypt(ks, m)
+    small = E.keyswitch(ev, ct)
+    ks_meas = _log2_std(E.decrypt_small(ks, small) - pt)
+    ks_model = 0.5 * math.log2(p.glwe_std ** 2 + P.variance_keyswitch(p.big_dim, p.ks_level, p.ks_base_log, p.lwe_std ** 2))
+    assert abs(ks_meas - ks_model) < 0.5, (ks_meas, ks_model)
+    luts = E.build_lut_accumulators(p, np.arange(1 << p.p)[None, :])
+    out = E.bootstrap(ev, small, E.from_np_u64(luts, cuda_device), None)
+    msg, ph = E.decrypt(ks, out, return_phase=True)
+    assert np.array_equal(msg, m)                      # zero errors over the batch (p_error ~1e-12)
+    out_meas = _log2_std(ph - pt)
+    out_model = 0.5 * math.log2(P.variance_pbs_out(p.n, p.k, p.N, p.pbs_level, p.pbs_base_log, p.glwe_std ** 2))
+    assert abs(out_meas - out_model) < 1.5, (out_meas, out_model)
+    # oracle on a subset of the same keyswitched inputs
+    ref = oracle.pbs(E.to_np_u64(small)[:oracle_n], oracle.bsk_to_fourier(E.to_np_u64(ks.bsk_std)), luts, None,
+                     p.pbs_base_log)
+    ph_ref = oracle.decrypt_phase(ref, E.to_np_u64(ks.sk_big))
+    assert np.array_equal(oracle.decode(ph_ref, p.p), m[:oracle_n])
+    var_gpu = 4.0 ** _log2_std(ph - pt)
+    var_ref = 4.0 ** _log2_std(ph_ref - pt[:oracle_n])
+    slack = 1.0 + 4.0 / math.sqrt(oracle_n)            # sampling error of the reference variance
+    assert var_gpu <= 2.0 * var_ref * slack, (var_gpu, var_ref)
+
+
+@pytest.mark.parametrize("bits", [1, 2, 3, 5, 7])
+def test_selected_parameters_error_rate(cuda_device, bits):
+    """Parameters picked by params.select_parameters for p_error=1e-6: no decoding error over 1024
+    lookups, measured bootstrap noise within 1.5 bits of the model."""
+    p = P.select_parameters(bits, 1.0, 1e-6)
+    ks = E.KeySet(p, cuda_device, seed=9)
+    ev = E.EvalKeys.of(ks)
+    rng = np.random.default_rng(bits)
+    B = 1024 if bits < 7 else 256
+    m = rng.integers(0, 1 << p.p, B).astype(np.uint64)
+    table = rng.integers(0, 1 << p.p, (1, 1 << p.p))
+    luts = E.from_np_u64(E.build_lut_accumulators(p, table), cuda_device)
+    out = E.table_lookup(ev, E.encrypt(ks, m), luts)
+    exp = table[0, m.astype(np.int64)].astype(np.uint64)
+    msg, ph = E.decrypt(ks, out, return_phase=True)
+    assert np.array_equal(msg, exp)
+    meas = _log2_std(ph - (exp << np.uint64(63 - p.p)))
+    model = 0.5 * math.log2(P.variance_pbs_out(p.n, p.k, p.N, p.pbs_level, p.pbs_base_log, p.glwe_std ** 2))
+    assert meas < model + 1.0, (meas, model)
