@@ -157,10 +157,19 @@ def _static_slices(offsets, sizes, strides):
 class Executor:
     """Runs one parsed program on one device with one parameter set."""
 
-    def __init__(self, program: Program, params: CryptoParams, device):
+    def __init__(self, program: Program, params: CryptoParams, device, group=None):
+        """`group`: optional torch.distributed process group.  With world size G > 1 every table
+        lookup is sharded BY CIPHERTEXT over the ranks (keys replicated per GPU) and the bootstrapped
+        rows are all-gathered (NCCL over NVLink on GPUs); the cheap linear ops stay replicated."""
         self.program = program
         self.params = params
         self.device = torch.device(device)
+        self.group = group
+        self.world, self.rank = 1, 0
+        if group is not None:
+            import torch.distributed as dist
+
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.L = params.ct_words
         self._plans: Dict[int, dict] = {}          # per-op cached host plans + device uploads
         self._consts: Dict[str, np.ndarray] = {}
@@ -312,8 +321,27 @@ class Executor:
             return {"luts": E.from_np_u64(acc, self.device), "idx": idx}
 
         plan = self._plan(op, build)
-        out = E.table_lookup(self._ev, x.data, plan["luts"], plan["idx"])
+        if self.world == 1:
+            out = E.table_lookup(self._ev, x.data, plan["luts"], plan["idx"])
+        else:
+            out = self._tlu_sharded(x.data, plan["luts"], plan["idx"])
         return Ct(out, op.result_type.dims)
+
+    def _tlu_sharded(self, rows: torch.Tensor, luts, idx):
+        """Rank r bootstraps rows [r*per, (r+1)*per) and all ranks gather the result."""
+        import torch.distributed as dist
+
+        n = rows.shape[0]
+        per = (n + self.world - 1) // self.world
+        lo = min(self.rank * per, n)
+        hi = min(lo + per, n)
+        mine = torch.zeros((per, self.L), dtype=torch.int64, device=rows.device)
+        if hi > lo:
+            sub_idx = None if idx is None else idx[lo:hi].contiguous()
+            mine[: hi - lo] = E.table_lookup(self._ev, rows[lo:hi].contiguous(), luts, sub_idx)
+        full = torch.empty((per * self.world, self.L), dtype=torch.int64, device=rows.device)
+        dist.all_gather_into_tensor(full, mine, group=self.group)
+        return full[:n].contiguous()
 
     # ---------------------------------------------------- clear-weighted linear ---
     def _gather(self, op: Op, x: Ct, build: Callable[[], Tuple[np.ndarray, np.ndarray, Optional[np.ndarray]]]) -> Ct:

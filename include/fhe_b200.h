@@ -1,0 +1,110 @@
+/*
+ * fhe_b200.h -- C ABI of the B200-native encrypted-execution backend (libfhe_b200.so).
+ *
+ * This is the drop-in boundary for the hot path behind concrete-numpy's Circuit.run / Server.run:
+ * the entry points a runtime for the reference's FHE / FHELinalg programs binds to.  In the
+ * reference the same role is played by the C runtime of the (absent) concrete-compiler wheel
+ * (`concretelang/Runtime/wrappers.cpp`: memref_keyswitch_lwe_u64, memref_bootstrap_lwe_u64,
+ * memref_batched_*, memref_add_lwe_ciphertexts_u64, ... -- SURVEY.md section 2.2), reached from
+ * concrete/numpy/compilation/server.py:286 (`self._support.server_call(...)`) and, for keys /
+ * encryption / decryption, from concrete/numpy/compilation/client.py:106, 178-182, 201.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (cudaMalloc / torch .data_ptr()), never freed or
+ *     reallocated by the library; `stream` is a cudaStream_t passed as void*;
+ *   - torus words are uint64_t (q = 2^64); an LWE ciphertext of dimension d is d mask words
+ *     followed by the body; tensors of ciphertexts are [E][d+1] row-major;
+ *   - every function returns 0 on success, 2 for invalid arguments, 3/4 for unsupported
+ *     shapes, 1000+cudaError_t for CUDA failures; fhe_last_error() returns the message of the
+ *     last failure on the calling thread;
+ *   - calls are asynchronous on `stream` (no device synchronisation inside), one host thread per
+ *     device.
+ */
+#ifndef FHE_B200_H
+#define FHE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- housekeeping ------------------------------------------------------------------- */
+const char* fhe_last_error(void);
+int fhe_abi_version(void);
+int fhe_device_info(int* sm_count, int* cc_major, int* cc_minor, long* total_mem);
+/* DFMA throughput of the current device in TFLOP/s (roofline denominator of the bootstrap) */
+int fhe_measure_fp64_peak(double* tflops, void* stream);
+
+/* ---- key generation: replaces ClientSupport.key_set (client.py:96-106) ---------------
+ * Keys are a pure function of (seed, parameters): counter-based ChaCha20 streams.
+ * domain: 1 = small LWE key (dimension n), 2 = big key (k*N, the flattened GLWE key). */
+int fhe_keygen_lwe_secret(uint64_t* sk, int dim, uint64_t seed, int domain, void* stream);
+/* KSK [kN][level][n+1]: row (i, lv) encrypts sk_big[i] * 2^(64-(lv+1)*base_log) under sk_small */
+int fhe_keygen_ksk(uint64_t* ksk, const uint64_t* sk_big, int kN, const uint64_t* sk_small, int n,
+                   int level, int base_log, double std, uint64_t seed, void* stream);
+/* standard-domain BSK [n][level][k+1][k+1][N]; scratch: >= k*N + k int32 words */
+int fhe_keygen_bsk(uint64_t* bsk, const uint64_t* sk_small, int n, const uint64_t* sk_glwe, int k,
+                   int N, int level, int base_log, double std, uint64_t seed, int* scratch,
+                   void* stream);
+/* Fourier-domain BSK conversion on device; layout owned by the bootstrap kernel.
+ * fhe_bsk_fourier_elems() = number of (re, im) double pairs of the output buffer. */
+int fhe_pbs_cluster_size(int N, int k, int level);
+long fhe_bsk_fourier_elems(int n, int k, int N, int level);
+int fhe_bsk_to_fourier(void* bsk_f /* double2* */, const uint64_t* bsk_std, int n, int k, int N,
+                       int level, int base_log, void* stream);
+
+/* ---- encrypt / decrypt: replace ClientSupport.encrypt_arguments / decrypt_result -----
+ * (client.py:178-182, 201).  plaintexts are already encoded (m << (63 - p)). */
+int fhe_encrypt_lwe_batch(uint64_t* ct /* [B][dim+1] */, const uint64_t* plaintexts /* [B] */,
+                          long B, const uint64_t* sk, int dim, double std, uint64_t seed,
+                          uint64_t first_index, void* stream);
+int fhe_trivial_lwe_batch(uint64_t* ct, const uint64_t* plaintexts, long B, int dim, void* stream);
+/* phase[e] = body - <a, s>; msg[e] = phase decoded at p bits + 1 padding bit (either may be NULL) */
+int fhe_decrypt_lwe_batch(uint64_t* phase, uint64_t* msg, const uint64_t* ct, long B,
+                          const uint64_t* sk, int dim, int p, void* stream);
+
+/* ---- table lookup = keyswitch + programmable bootstrap -------------------------------
+ * replace memref_batched_keyswitch_lwe_u64 / memref_batched_bootstrap_lwe_u64 for
+ * FHE.apply_lookup_table, FHELinalg.apply_lookup_table, apply_mapped_lookup_table
+ * (concrete/numpy/mlir/node_converter.py:1190-1206). */
+int fhe_keyswitch_batch(uint64_t* out /* [B][n+1] */, const uint64_t* in /* [B][kN+1] */, long B,
+                        const uint64_t* ksk, int kN, int n, int level, int base_log, void* stream);
+int fhe_pbs_batch(uint64_t* out /* [B][kN+1] */, const uint64_t* in /* [B][n+1] */, long B,
+                  const void* bsk_f, const uint64_t* luts /* [T][(k+1)N] accumulators */,
+                  const int* lut_idx /* [B] or NULL */, int n, int k, int N, int level, int base_log,
+                  void* stream);
+
+/* ---- torus linear algebra on [E][L] tensors (L = kN+1) --------------------------------
+ * ia / ib: optional int32 row maps (numpy broadcasting resolved by the host), NULL = identity.
+ * FHE.add_eint / FHELinalg.add_eint (node_converter.py:216-242) ... */
+int fhe_lin_add(uint64_t* out, const uint64_t* a, const uint64_t* b, const int* ia, const int* ib,
+                long E, int L, void* stream);
+int fhe_lin_sub(uint64_t* out, const uint64_t* a, const uint64_t* b, const int* ia, const int* ib,
+                long E, int L, void* stream);
+int fhe_lin_neg(uint64_t* out, const uint64_t* a, const int* ia, long E, int L, void* stream);
+/* add_eint_int / sub_eint_int: out[e] = a[ia[e]], body += pt[e] (encoded plaintext) */
+int fhe_lin_add_plain(uint64_t* out, const uint64_t* a, const int* ia, const uint64_t* pt, long E,
+                      int L, void* stream);
+/* sub_int_eint: out[e] = pt[e] - a[ia[e]] */
+int fhe_lin_plain_sub(uint64_t* out, const uint64_t* a, const int* ia, const uint64_t* pt, long E,
+                      int L, void* stream);
+/* mul_eint_int (node_converter.py:630-650): every word times the signed clear c[e] */
+int fhe_lin_mul_clear(uint64_t* out, const uint64_t* a, const int* ia, const int64_t* c, long E,
+                      int L, void* stream);
+/* general clear-weighted gather (dot / matmul / conv2d / sum, node_converter.py:436-524, 596-616,
+ * 1094-1127): out[e] = sum_j w[e][j] * x[idx[e][j]] (+ bias[e] on the body); idx < 0 = no term */
+int fhe_lin_gather_mac(uint64_t* out, const uint64_t* x, const int* idx, const int64_t* w,
+                       const uint64_t* bias, long E, int K, int L, void* stream);
+/* FHELinalg.matmul_eint_int on a plain 2-D problem: x [Mr][K][L], W [K][Nc] -> out [Mr][Nc][L] */
+int fhe_matmul_ct_clear(uint64_t* out, const uint64_t* x, const int64_t* W, long Mr, int K, int Nc,
+                        int L, void* stream);
+
+/* ---- test hook: negacyclic product through the fp64 FFT path --------------------------- */
+int fhe_debug_polymul(uint64_t* out, const int64_t* a_small, const uint64_t* b_torus, long npoly,
+                      int N, int k, int level, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FHE_B200_H */

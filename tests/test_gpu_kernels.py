@@ -127,8 +127,8 @@ PBS_CASES = [
 
 @pytest.mark.parametrize("p_bits,n,k,N,level,base_log", PBS_CASES)
 def test_pbs_matches_oracle(oracle, cuda_device, p_bits, n, k, N, level, base_log):
-    p = E.CryptoParams(p=p_bits, n=n, k=k, N=N, pbs_level=level, pbs_base_log=base_log, ks_level=4,
-                       ks_base_log=4, lwe_std=2.0 ** -40, glwe_std=2.0 ** -55)
+    p = E.CryptoParams(p=p_bits, n=n, k=k, N=N, pbs_level=level, pbs_base_log=base_log, ks_level=8,
+                       ks_base_log=3, lwe_std=2.0 ** -40, glwe_std=2.0 ** -55)
     ks = E.KeySet(p, cuda_device, seed=5, keep_std_bsk=True)
     ev = E.EvalKeys.of(ks)
     rng = np.random.default_rng(p_bits)
