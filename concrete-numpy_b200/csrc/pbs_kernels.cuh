@@ -1,0 +1,708 @@
+// Batched programmable bootstrap for sm_100a -- kernel templates.
+//
+// One thread-block cluster of C CTAs per ciphertext (C = 1 for N <= 4096); the whole blind rotation
+// (n CMUX iterations) runs on-chip:
+//
+//   * ACC (k+1 torus polynomials) lives in shared memory, split over the C CTAs in a "comb"
+//     layout: CTA `rank` owns coefficients  h*M + j1*L1 + rank*Q + q  (h<2, j1<R1, q<Q),
+//     M = N/2 = R1*L1, Q = L1/C.  (C == 1: R1 is simply the radix of the first FFT stage.)
+//   * Negacyclic product through an fp64 FFT of M complex points (fold + twist), factored as
+//       stage 1 : radix-R1 butterflies over j1, fused with rotate/subtract/decompose; all inputs are
+//                 CTA-local thanks to the comb layout, outputs go straight to the CTA that owns
+//                 sub-transform t1 (distributed shared memory when C > 1);
+//       mid     : one or two radix-16/8 passes in shared memory, register butterflies, twiddles in
+//                 shared memory and re-used across the J = (k+1)*level buffers;
+//       fused   : last radix-RF pass + multiply-accumulate against GGSW_i + first inverse pass, all
+//                 in registers (GGSW streamed from L2 with coalesced, software-pipelined loads);
+//       then the mirrored inverse passes, and the inverse radix-R1 stage fused with untwist /
+//       round-to-torus / ACC update.
+//   * The spectrum never leaves its (digit-reversed, thread-major) order: fhe_bsk_to_fourier runs the
+//     same forward code, so the pointwise product needs no permutation.
+//   * modulus switch is fused at the top, sample extract at the bottom.
+//
+// Replaces memref_batched_bootstrap_lwe_u64 of the absent concrete-compiler runtime; reached from
+// concrete/numpy/compilation/server.py:286 for every FHE.apply_lookup_table the reference emits
+// (concrete/numpy/mlir/node_converter.py:1129-1208).
+#pragma once
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+namespace cg = cooperative_groups;
+
+#define PBS_SMEM_MAX 232448  // 227 KB opt-in dynamic shared memory per CTA on sm_100
+
+struct PbsGeom {
+    int n, k, N, level, base_log;
+    int logN, logM;
+    int J;                // (k+1)*level forward transforms per CMUX
+    double inv_M;
+    double2 cj[16];       // exp(i*pi*j1/(2*R1)), j1 < R1
+};
+
+// Compile-time FFT plan.  M = R1 * L1, L1 = RA * RB * RF (RA / RB = 1 when absent).
+template <int C_, int LOGR1_, int LRA_, int LRB_, int LRF_, int NT_, int MINB_, int KMAX_>
+struct PbsPlan {
+    static constexpr int C = C_, LOGC = (C_ == 1 ? 0 : C_ == 2 ? 1 : C_ == 4 ? 2 : 3);
+    static constexpr int LOGR1 = LOGR1_, R1 = 1 << LOGR1_;
+    static constexpr int LRA = LRA_, LRB = LRB_, LRF = LRF_, RF = 1 << LRF_;
+    static constexpr int NT = NT_, MINB = MINB_, KMAX = KMAX_;
+    static constexpr int LOGL1 = LRA_ + LRB_ + LRF_, L1 = 1 << LOGL1;
+    static constexpr int LOGM = LOGR1_ + LOGL1, M = 1 << LOGM, N = 2 << LOGM;
+    static constexpr int LOGBUF = (C_ > 1) ? LOGL1 : LOGM, BUF = 1 << LOGBUF;   // double2 per work buffer per CTA
+    static constexpr int LOGQ = LOGL1 - LOGC, Q = 1 << LOGQ;
+    static constexpr int LOGS = LOGM + 1 - LOGC, S = 1 << LOGS;                  // ACC words per polynomial per CTA
+    static constexpr int SA = 1 << (LOGL1 - LRA_);        // stride of mid pass A (sub-length L1)
+    static constexpr int SB = 1 << LRF_;                  // stride of mid pass B (sub-length L1 / RA)
+    static constexpr int TWA = LRA_ ? ((1 << LRA_) - 1) * SA : 0;
+    static constexpr int TWB = LRB_ ? ((1 << LRB_) - 1) * SB : 0;
+    static constexpr int TWN = TWA + TWB;                 // shared twiddle entries
+    static_assert(C_ == 1 || LOGR1_ == LOGC, "cluster plans use R1 == C");
+    static_assert(LRA_ > 0 || LRB_ == 0, "pass B requires pass A");
+};
+
+struct PbsPlanMeta {       // what the host needs to know about a plan
+    int C, logR1, lra, lrb, lrf, NT, minb, kmax, logM;
+    long smem_fixed;       // twiddle bytes
+};
+
+// ---- small complex helpers -----------------------------------------------------------
+__device__ __forceinline__ int SW(int i) { return i ^ ((i >> 3) & 7); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {  // a * conj(b)
+    return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+template <bool INV>
+__device__ __forceinline__ double2 mul_mi(double2 a) {  // * (-i) forward, * (+i) inverse
+    return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+}
+// * exp(-+ i*pi/4): (1 -+ i)/sqrt2
+template <bool INV>
+__device__ __forceinline__ double2 mul_w8(double2 a) {
+    const double h = 0.70710678118654752440;
+    return INV ? make_double2((a.x - a.y) * h, (a.x + a.y) * h) : make_double2((a.x + a.y) * h, (a.y - a.x) * h);
+}
+// * exp(-+ 3*i*pi/4): (-1 -+ i)/sqrt2
+template <bool INV>
+__device__ __forceinline__ double2 mul_w8_3(double2 a) {
+    const double h = 0.70710678118654752440;
+    return INV ? make_double2(-(a.x + a.y) * h, (a.x - a.y) * h) : make_double2((a.y - a.x) * h, -(a.x + a.y) * h);
+}
+
+// natural-order in/out DFTs of size R in registers; forward kernel exp(-2*pi*i*r*m/R)
+template <int R, bool INV>
+struct Dft;
+template <bool INV>
+struct Dft<1, INV> {
+    static __device__ __forceinline__ void run(double2*) {}
+};
+template <bool INV>
+struct Dft<2, INV> {
+    static __device__ __forceinline__ void run(double2* x) {
+        double2 a = x[0], b = x[1];
+        x[0] = cadd(a, b);
+        x[1] = csub(a, b);
+    }
+};
+template <bool INV>
+struct Dft<4, INV> {
+    static __device__ __forceinline__ void run(double2* x) {
+        double2 t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]);
+        double2 t2 = cadd(x[1], x[3]), t3 = mul_mi<INV>(csub(x[1], x[3]));
+        x[0] = cadd(t0, t2);
+        x[1] = cadd(t1, t3);
+        x[2] = csub(t0, t2);
+        x[3] = csub(t1, t3);
+    }
+};
+template <bool INV>
+struct Dft<8, INV> {
+    static __device__ __forceinline__ void run(double2* x) {
+        double2 e[4] = {x[0], x[2], x[4], x[6]};
+        double2 o[4] = {x[1], x[3], x[5], x[7]};
+        Dft<4, INV>::run(e);
+        Dft<4, INV>::run(o);
+        const double2 o1 = mul_w8<INV>(o[1]), o2 = mul_mi<INV>(o[2]), o3 = mul_w8_3<INV>(o[3]);
+        x[0] = cadd(e[0], o[0]); x[4] = csub(e[0], o[0]);
+        x[1] = cadd(e[1], o1);   x[5] = csub(e[1], o1);
+        x[2] = cadd(e[2], o2);   x[6] = csub(e[2], o2);
+        x[3] = cadd(e[3], o3);   x[7] = csub(e[3], o3);
+    }
+};
+// 16 = 4 x 4:  r = 4a + b, m = c + 4d:  W16^{rm} = W4^{ac} * W16^{bc} * W4^{bd}
+template <bool INV>
+struct Dft<16, INV> {
+    static __device__ __forceinline__ void run(double2* x) {
+        const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;   // cos, sin(pi/8)
+        double2 u[4][4];   // u[b][c]
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            double2 t[4] = {x[b], x[4 + b], x[8 + b], x[12 + b]};
+            Dft<4, INV>::run(t);
+#pragma unroll
+            for (int c = 0; c < 4; c++) u[b][c] = t[c];
+        }
+        // twiddles W16^{bc} (conjugated for the inverse)
+        const double2 w1 = make_double2(c1, INV ? s1 : -s1);     // W16^1
+        const double2 w3 = make_double2(s1, INV ? c1 : -c1);     // W16^3
+        const double2 w9 = make_double2(-c1, INV ? -s1 : s1);    // W16^9
+        u[1][1] = cmul(u[1][1], w1);
+        u[1][2] = mul_w8<INV>(u[1][2]);                          // W16^2
+        u[1][3] = cmul(u[1][3], w3);
+        u[2][1] = mul_w8<INV>(u[2][1]);                          // W16^2
+        u[2][2] = mul_mi<INV>(u[2][2]);                          // W16^4
+        u[2][3] = mul_w8_3<INV>(u[2][3]);                        // W16^6
+        u[3][1] = cmul(u[3][1], w3);
+        u[3][2] = mul_w8_3<INV>(u[3][2]);                        // W16^6
+        u[3][3] = cmul(u[3][3], w9);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            double2 t[4] = {u[0][c], u[1][c], u[2][c], u[3][c]};
+            Dft<4, INV>::run(t);
+#pragma unroll
+            for (int d = 0; d < 4; d++) x[c + 4 * d] = t[d];
+        }
+    }
+};
+
+// ---- cluster helpers ---------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void csync() {
+    if (C == 1) __syncthreads();
+    else cg::this_cluster().sync();
+}
+template <int C, typename T>
+__device__ __forceinline__ T* peer(T* p, int rank) {
+    if (C == 1) return p;
+    return cg::this_cluster().map_shared_rank(p, rank);
+}
+
+__device__ __forceinline__ u64 f2torus(double x) {
+    x -= 18446744073709551616.0 * rint(x * 5.42101086242752217e-20);
+    return (u64)__double2ll_rn(x);
+}
+__device__ __forceinline__ int modswitch(u64 x, int logN) {  // -> Z_{2N}
+    const int lg = logN + 1;
+    u64 t = ((x >> (64 - lg - 1)) + 1) >> 1;
+    return (int)(t & ((1ULL << lg) - 1));
+}
+
+// ---- one mid pass over `nbuf` buffers of BUF points, sub-transform length 2^LOGLC ------------
+// forward (DIF): y_m = DFT_R(x)_m * W_Lc^{q m};   inverse (DIT): mirror with conjugates.
+// A thread keeps the R-1 twiddles of its butterfly index in registers across the buffers it handles.
+template <int LR, int LOGLC, int LOGBUF, int NT, bool INV>
+__device__ __forceinline__ void mid_pass(double2* __restrict__ work, int nbuf,
+                                         const double2* __restrict__ tw /* shared: [(R-1)][S] */) {
+    constexpr int R = 1 << LR;
+    constexpr int LOGSS = LOGLC - LR, SS = 1 << LOGSS;          // stride inside a sub-transform
+    constexpr int NBF = 1 << (LOGBUF - LR);                     // butterflies per buffer
+    constexpr int WPT = (NBF >= NT) ? NBF / NT : 1;             // butterfly indices per thread
+    constexpr int GROUPS = (NBF >= NT) ? 1 : NT / NBF;          // thread groups sharing the buffers
+    const int grp = (GROUPS > 1) ? (int)(threadIdx.x / NBF) : 0;
+#pragma unroll 1
+    for (int it = 0; it < WPT; it++) {
+        const int w = (GROUPS > 1) ? (int)(threadIdx.x % NBF) : (int)threadIdx.x + it * NT;
+        const int b = w >> LOGSS, q = w & (SS - 1);
+        const int pos0 = (b << LOGLC) + q;
+        double2 t[R];
+#pragma unroll
+        for (int m = 1; m < R; m++) t[m] = tw[((m - 1) << LOGSS) + q];
+#pragma unroll 1
+        for (int buf = grp; buf < nbuf; buf += GROUPS) {
+            double2* base = work + ((size_t)buf << LOGBUF);
+            double2 x[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) x[r] = base[SW(pos0 + (r << LOGSS))];
+            if (!INV) {
+                Dft<R, false>::run(x);
+#pragma unroll
+                for (int m = 1; m < R; m++) x[m] = cmul(x[m], t[m]);
+            } else {
+#pragma unroll
+                for (int m = 1; m < R; m++) x[m] = cmulc(x[m], t[m]);
+                Dft<R, true>::run(x);
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) base[SW(pos0 + (r << LOGSS))] = x[r];
+        }
+    }
+}
+
+template <class P, bool INV>
+__device__ __forceinline__ void mid_passes(double2* work, int nbuf, const double2* tw_s) {
+    if (!INV) {
+        if (P::LRA) {
+            mid_pass<P::LRA, P::LOGL1, P::LOGBUF, P::NT, false>(work, nbuf, tw_s);
+            __syncthreads();
+        }
+        if (P::LRB) {
+            mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, P::NT, false>(work, nbuf, tw_s + P::TWA);
+            __syncthreads();
+        }
+    } else {
+        if (P::LRB) {
+            mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, P::NT, true>(work, nbuf, tw_s + P::TWA);
+            __syncthreads();
+        }
+        if (P::LRA) {
+            mid_pass<P::LRA, P::LOGL1, P::LOGBUF, P::NT, true>(work, nbuf, tw_s);
+            __syncthreads();
+        }
+    }
+}
+
+// ---- stage 1 output: twist, radix-R1 butterfly, stage twiddle, store to the owner of t1 ---------
+// re/im: folded inputs of one item (j1 < R1); T: exp(i*pi*j2*(1-4*t1)/N); dst: local address of
+// element j2 of the destination buffer (C > 1) or of element (t1 = 0, j2) (C == 1).
+template <class P>
+__device__ __forceinline__ void stage1_emit(double2* dst_buf, int j2, const double* re, const double* im,
+                                            const double2* T, const PbsGeom& g) {
+    double2 z[P::R1];
+#pragma unroll
+    for (int j1 = 0; j1 < P::R1; j1++) {
+        const double2 d = make_double2(re[j1], im[j1]);
+        z[j1] = (j1 == 0) ? d : cmul(d, g.cj[j1]);
+    }
+    Dft<P::R1, false>::run(z);
+#pragma unroll
+    for (int t1 = 0; t1 < P::R1; t1++) {
+        const double2 v = cmul(z[t1], T[t1]);
+        if (P::C > 1) *peer<P::C>(dst_buf + SW(j2), t1) = v;
+        else dst_buf[SW((t1 << P::LOGL1) + j2)] = v;
+    }
+}
+
+// inverse of stage 1 for one item: gather sub-transform outputs, conj twiddle, inverse butterfly, untwist
+template <class P>
+__device__ __forceinline__ void stage1_gather(const double2* src_buf, int j2, const double2* T, const PbsGeom& g,
+                                              double2* z /* [R1]: (coef j1*L1+j2, coef M+j1*L1+j2), unnormalised */) {
+    double2 v[P::R1];
+#pragma unroll
+    for (int t1 = 0; t1 < P::R1; t1++) {
+        if (P::C > 1) v[t1] = *peer<P::C>(src_buf + SW(j2), t1);
+        else v[t1] = src_buf[SW((t1 << P::LOGL1) + j2)];
+    }
+#pragma unroll
+    for (int t1 = 0; t1 < P::R1; t1++) v[t1] = cmulc(v[t1], T[t1]);
+    Dft<P::R1, true>::run(v);
+#pragma unroll
+    for (int j1 = 0; j1 < P::R1; j1++) z[j1] = (j1 == 0) ? v[0] : cmulc(v[j1], g.cj[j1]);
+}
+
+template <class P>
+__device__ __forceinline__ void load_T(double2* T, const double2* __restrict__ twT, int j2) {
+#pragma unroll
+    for (int t1 = 0; t1 < P::R1; t1++) T[t1] = __ldg(&twT[((size_t)t1 << P::LOGL1) + j2]);
+}
+
+// slot (index inside one polynomial's CTA slice) -> coefficient index
+template <class P>
+__device__ __forceinline__ int slot_to_coef(int s, int rank) {
+    const int q = s & (P::Q - 1);
+    const int hj = s >> P::LOGQ;                 // h*R1 + j1
+    return (hj << P::LOGL1) + (rank << P::LOGQ) + q;
+}
+
+// Fourier BSK layout: [i][j][o][rank][r][w]  (w = butterfly group of the fused pass, r < RF)
+template <class P>
+__device__ __forceinline__ size_t ggsw_slice(int j, int o, int k, int rank) {
+    return (((size_t)(j * (k + 1) + o) * P::C + rank) << P::LOGBUF);
+}
+
+// ---- the bootstrap kernel ------------------------------------------------------------------
+template <class P>
+__global__ void __launch_bounds__(P::NT, P::MINB)
+k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* __restrict__ bskF,
+      const u64* __restrict__ luts, const int* __restrict__ lut_idx, const PbsGeom g,
+      const double2* __restrict__ twT, const double2* __restrict__ tw_mid) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int C = P::C, R1 = P::R1, NT = P::NT, RF = P::RF, BUF = P::BUF, Q = P::Q, S = P::S;
+    constexpr int N = P::N, M = P::M;
+    constexpr int NG = BUF / RF;                    // butterfly groups of the fused pass
+    const int k = g.k, level = g.level, J = g.J, base_log = g.base_log;
+    u64* acc = reinterpret_cast<u64*>(smem_raw);                                   // [(k+1)][S]
+    double2* work = reinterpret_cast<double2*>(acc + (size_t)(k + 1) * S);         // [J][BUF]
+    double2* tw_s = work + (size_t)J * BUF;                                        // [TWN]
+    const int tid = threadIdx.x;
+    int rank = 0;
+    if (C > 1) rank = (int)cg::this_cluster().block_rank();
+    const long cluster_id = blockIdx.x / C, nclusters = gridDim.x / C;
+    const size_t ggsw_stride = (size_t)J * (k + 1) * C * BUF;   // double2 per CMUX iteration
+    const u64 mask = (1ULL << base_log) - 1;
+    const int nonrep = 64 - level * base_log;
+
+    for (int t = tid; t < P::TWN; t += NT) tw_s[t] = tw_mid[t];
+
+    for (long ct = cluster_id; ct < B; ct += nclusters) {
+        const u64* lwe = in + (size_t)ct * (g.n + 1);
+        const u64* lut = luts + (size_t)(lut_idx ? lut_idx[ct] : 0) * (k + 1) * N;
+        // ---- ACC = X^{-b~} * LUT
+        {
+            const int a0 = (2 * N - modswitch(lwe[g.n], g.logN)) & (2 * N - 1);
+            for (int w = tid; w < (k + 1) * S; w += NT) {
+                const int c = w >> P::LOGS, s = w & (S - 1);
+                const int v = (slot_to_coef<P>(s, rank) - a0) & (2 * N - 1);
+                const u64 x = lut[(size_t)c * N + (v & (N - 1))];
+                acc[w] = (v >> (P::LOGM + 1)) ? (0ULL - x) : x;
+            }
+        }
+        int a_next = modswitch(lwe[0], g.logN);
+        csync<C>();
+
+        for (int i = 0; i < g.n; i++) {
+            const int a = a_next;
+            a_next = (i + 1 < g.n) ? modswitch(lwe[i + 1], g.logN) : 0;
+            // ---- P1: rotate, subtract, decompose, fold+twist, radix-R1 stage, scatter to owners
+#pragma unroll 1
+            for (int it = tid; it < ((k + 1) << P::LOGQ); it += NT) {
+                const int c = it >> P::LOGQ, q = it & (Q - 1);
+                const int j2 = (rank << P::LOGQ) + q;
+                const u64* accc = acc + ((size_t)c << P::LOGS);
+                double2 T[R1];
+                load_T<P>(T, twT, j2);
+                u64 st[2 * R1];
+                {
+                    const int base = (j2 - a) & (2 * N - 1);
+                    u64 rv[2 * R1];
+                    unsigned negm = 0;
+#pragma unroll
+                    for (int hj = 0; hj < 2 * R1; hj++) {
+                        const int v = (base + (hj << P::LOGL1)) & (2 * N - 1);
+                        const int idx = v & (N - 1);
+                        negm |= (unsigned)(v >> (P::LOGM + 1)) << hj;
+                        const int jj2 = idx & (P::L1 - 1);
+                        const int slot = ((idx >> P::LOGL1) << P::LOGQ) + (jj2 & (Q - 1));
+                        rv[hj] = *peer<C>(accc + slot, jj2 >> P::LOGQ);
+                    }
+#pragma unroll
+                    for (int hj = 0; hj < 2 * R1; hj++) {
+                        const u64 own = accc[(hj << P::LOGQ) + q];
+                        const u64 diff = (((negm >> hj) & 1) ? (0ULL - rv[hj]) : rv[hj]) - own;
+                        st[hj] = ((diff >> (nonrep - 1)) + 1) >> 1;      // closest representable
+                    }
+                }
+#pragma unroll 1
+                for (int t = 0; t < level; t++) {
+                    const int lv = level - 1 - t;       // digits come out least significant level first
+                    double re[R1], im[R1];
+#pragma unroll
+                    for (int hj = 0; hj < 2 * R1; hj++) {
+                        u64 res = st[hj] & mask;
+                        u64 s2 = st[hj] >> base_log;
+                        u64 carry = (((res - 1) | s2) & res) >> (base_log - 1);
+                        st[hj] = s2 + carry;
+                        const double d = (double)((i64)res - (i64)(carry << base_log));
+                        if (hj < R1) re[hj] = d;
+                        else im[hj - R1] = d;
+                    }
+                    stage1_emit<P>(work + ((size_t)(c * level + lv) << P::LOGBUF), j2, re, im, T, g);
+                }
+            }
+            csync<C>();
+            // ---- P2: mid passes of all J buffers
+            mid_passes<P, false>(work, J, tw_s);
+            // ---- P3: last forward pass + multiply-accumulate against GGSW_i + first inverse pass
+            {
+                const double2* gg = bskF + (size_t)i * ggsw_stride;
+#pragma unroll 1
+                for (int w = tid; w < NG; w += NT) {
+                    double2 r[P::KMAX + 1][RF];
+#pragma unroll
+                    for (int o = 0; o <= P::KMAX; o++)
+#pragma unroll
+                        for (int m = 0; m < RF; m++) r[o][m] = make_double2(0.0, 0.0);
+                    double2 gA[P::KMAX + 1][RF], gB[P::KMAX + 1][RF];
+                    auto load_g = [&](double2(&dst)[P::KMAX + 1][RF], int j) {
+#pragma unroll
+                        for (int o = 0; o <= P::KMAX; o++)
+                            if (o <= k) {
+                                const double2* p = gg + ggsw_slice<P>(j, o, k, rank) + w;
+#pragma unroll
+                                for (int m = 0; m < RF; m++) dst[o][m] = __ldg(p + m * NG);
+                            }
+                    };
+                    auto mac = [&](const double2(&gv)[P::KMAX + 1][RF], int j) {
+                        double2 x[RF];
+                        const double2* base = work + ((size_t)j << P::LOGBUF);
+#pragma unroll
+                        for (int m = 0; m < RF; m++) x[m] = base[SW(w * RF + m)];
+                        Dft<RF, false>::run(x);
+#pragma unroll
+                        for (int o = 0; o <= P::KMAX; o++)
+                            if (o <= k) {
+#pragma unroll
+                                for (int m = 0; m < RF; m++) {
+                                    r[o][m].x = fma(x[m].x, gv[o][m].x, r[o][m].x);
+                                    r[o][m].x = fma(-x[m].y, gv[o][m].y, r[o][m].x);
+                                    r[o][m].y = fma(x[m].x, gv[o][m].y, r[o][m].y);
+                                    r[o][m].y = fma(x[m].y, gv[o][m].x, r[o][m].y);
+                                }
+                            }
+                    };
+                    load_g(gA, 0);
+#pragma unroll 1
+                    for (int j = 0; j < J; j += 2) {
+                        if (j + 1 < J) load_g(gB, j + 1);
+                        mac(gA, j);
+                        if (j + 2 < J) load_g(gA, j + 2);
+                        if (j + 1 < J) mac(gB, j + 1);
+                    }
+#pragma unroll
+                    for (int o = 0; o <= P::KMAX; o++)
+                        if (o <= k) {
+                            Dft<RF, true>::run(r[o]);
+                            double2* base = work + ((size_t)o << P::LOGBUF);
+#pragma unroll
+                            for (int m = 0; m < RF; m++) base[SW(w * RF + m)] = r[o][m];
+                        }
+                }
+            }
+            __syncthreads();
+            // ---- P4: inverse mid passes of the k+1 output buffers
+            mid_passes<P, true>(work, k + 1, tw_s);
+            if (C > 1) csync<C>();
+            // ---- P5: gather from owners, inverse radix-R1 stage, untwist, round, ACC +=
+#pragma unroll 1
+            for (int it = tid; it < ((k + 1) << P::LOGQ); it += NT) {
+                const int o = it >> P::LOGQ, q = it & (Q - 1);
+                const int j2 = (rank << P::LOGQ) + q;
+                double2 T[R1];
+                load_T<P>(T, twT, j2);
+                double2 z[R1];
+                stage1_gather<P>(work + ((size_t)o << P::LOGBUF), j2, T, g, z);
+                u64* acco = acc + ((size_t)o << P::LOGS);
+#pragma unroll
+                for (int j1 = 0; j1 < R1; j1++) {
+                    acco[(j1 << P::LOGQ) + q] += f2torus(z[j1].x * g.inv_M);
+                    acco[((R1 + j1) << P::LOGQ) + q] += f2torus(z[j1].y * g.inv_M);
+                }
+            }
+            csync<C>();
+        }
+        // ---- sample extract coefficient 0
+        {
+            u64* o = out + (size_t)ct * ((size_t)k * N + 1);
+            for (int w = tid; w < (k + 1) * S; w += NT) {
+                const int c = w >> P::LOGS, s = w & (S - 1);
+                const int j = slot_to_coef<P>(s, rank);
+                const u64 v = acc[w];
+                if (c < k) {
+                    if (j == 0) o[(size_t)c * N] = v;
+                    else o[(size_t)c * N + (N - j)] = 0ULL - v;
+                } else if (j == 0)
+                    o[(size_t)k * N] = v;
+            }
+        }
+        // the same thread re-initialises the same ACC words at the top of the loop
+    }
+}
+
+// forward transform of one polynomial held as folded (re, im) inputs by the caller's functor:
+// stage 1 for every item of this CTA, cluster sync, mid passes.  Leaves buffer `buf` ready for the
+// last radix-RF pass.
+template <class P, class Src>
+__device__ __forceinline__ void forward_poly(double2* work, int buf, int rank, const PbsGeom& g,
+                                             const double2* __restrict__ twT, Src src) {
+#pragma unroll 1
+    for (int q = threadIdx.x; q < P::Q; q += P::NT) {
+        const int j2 = (rank << P::LOGQ) + q;
+        double2 T[P::R1];
+        load_T<P>(T, twT, j2);
+        double re[P::R1], im[P::R1];
+#pragma unroll
+        for (int j1 = 0; j1 < P::R1; j1++) {
+            re[j1] = src((j1 << P::LOGL1) + j2);
+            im[j1] = src(P::M + (j1 << P::LOGL1) + j2);
+        }
+        stage1_emit<P>(work + ((size_t)buf << P::LOGBUF), j2, re, im, T, g);
+    }
+}
+
+// ---- standard-domain BSK -> Fourier BSK (same transform, same layout as the MAC reads) --
+// in : [n][level][k+1 rows r][k+1 polys o][N] u64
+// out: [n][J = r*level+lv][o][C ranks][RF][NG] double2
+template <class P>
+__global__ void __launch_bounds__(P::NT, P::MINB)
+k_bsk_fourier(double2* __restrict__ outF, const u64* __restrict__ bsk, long npoly, const PbsGeom g,
+              const double2* __restrict__ twT, const double2* __restrict__ tw_mid) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int C = P::C, NT = P::NT, RF = P::RF, BUF = P::BUF, N = P::N;
+    constexpr int NG = BUF / RF;
+    double2* work = reinterpret_cast<double2*>(smem_raw);   // [BUF]
+    double2* tw_s = work + BUF;
+    const int k = g.k, level = g.level;
+    int rank = 0;
+    if (C > 1) rank = (int)cg::this_cluster().block_rank();
+    const long cluster_id = blockIdx.x / C, nclusters = gridDim.x / C;
+    for (int t = threadIdx.x; t < P::TWN; t += NT) tw_s[t] = tw_mid[t];
+    csync<C>();
+    for (long p = cluster_id; p < npoly; p += nclusters) {
+        const u64* src = bsk + (size_t)p * N;
+        forward_poly<P>(work, 0, rank, g, twT, [&](int coef) { return (double)(i64)src[coef]; });
+        csync<C>();
+        mid_passes<P, false>(work, 1, tw_s);
+        // p = ((i*level + lv)*(k+1) + r)*(k+1) + o
+        const int o = (int)(p % (k + 1));
+        const int r = (int)((p / (k + 1)) % (k + 1));
+        const int lv = (int)((p / ((long)(k + 1) * (k + 1))) % level);
+        const long i = p / ((long)(k + 1) * (k + 1) * level);
+        const int j = r * level + lv;
+        double2* dst = outF + (size_t)i * ((size_t)g.J * (k + 1) * C * BUF) + ggsw_slice<P>(j, o, k, rank);
+        for (int w = threadIdx.x; w < NG; w += NT) {
+            double2 x[RF];
+#pragma unroll
+            for (int m = 0; m < RF; m++) x[m] = work[SW(w * RF + m)];
+            Dft<RF, false>::run(x);
+#pragma unroll
+            for (int m = 0; m < RF; m++) dst[m * NG + w] = x[m];
+        }
+        csync<C>();
+    }
+}
+
+// ---- debug / test entry: out = a_small * b_torus in Z_2^64[X]/(X^N+1) through the same fp64
+// pipeline (forward both, pointwise product in the fused pass, inverse).  Used by tests to validate
+// the transform against an exact integer negacyclic product.
+template <class P>
+__global__ void __launch_bounds__(P::NT, P::MINB)
+k_polymul_test(u64* __restrict__ out, const i64* __restrict__ a_small, const u64* __restrict__ b_torus,
+               long npoly, const PbsGeom g, const double2* __restrict__ twT,
+               const double2* __restrict__ tw_mid) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int C = P::C, R1 = P::R1, NT = P::NT, RF = P::RF, BUF = P::BUF, N = P::N, M = P::M, Q = P::Q;
+    constexpr int NG = BUF / RF;
+    double2* work = reinterpret_cast<double2*>(smem_raw);   // [2][BUF]
+    double2* tw_s = work + 2 * BUF;
+    int rank = 0;
+    if (C > 1) rank = (int)cg::this_cluster().block_rank();
+    const long cluster_id = blockIdx.x / C, nclusters = gridDim.x / C;
+    for (int t = threadIdx.x; t < P::TWN; t += NT) tw_s[t] = tw_mid[t];
+    csync<C>();
+    for (long p = cluster_id; p < npoly; p += nclusters) {
+        const i64* pa = a_small + (size_t)p * N;
+        const u64* pb = b_torus + (size_t)p * N;
+        forward_poly<P>(work, 0, rank, g, twT, [&](int coef) { return (double)pa[coef]; });
+        forward_poly<P>(work, 1, rank, g, twT, [&](int coef) { return (double)(i64)pb[coef]; });
+        csync<C>();
+        mid_passes<P, false>(work, 2, tw_s);
+        for (int w = threadIdx.x; w < NG; w += NT) {
+            double2 x[RF], y[RF];
+#pragma unroll
+            for (int m = 0; m < RF; m++) {
+                x[m] = work[SW(w * RF + m)];
+                y[m] = work[BUF + SW(w * RF + m)];
+            }
+            Dft<RF, false>::run(x);
+            Dft<RF, false>::run(y);
+#pragma unroll
+            for (int m = 0; m < RF; m++) x[m] = cmul(x[m], y[m]);
+            Dft<RF, true>::run(x);
+#pragma unroll
+            for (int m = 0; m < RF; m++) work[SW(w * RF + m)] = x[m];
+        }
+        __syncthreads();
+        mid_passes<P, true>(work, 1, tw_s);
+        csync<C>();
+        for (int q = threadIdx.x; q < Q; q += NT) {
+            const int j2 = (rank << P::LOGQ) + q;
+            double2 T[R1];
+            load_T<P>(T, twT, j2);
+            double2 z[R1];
+            stage1_gather<P>(work, j2, T, g, z);
+#pragma unroll
+            for (int j1 = 0; j1 < R1; j1++) {
+                out[(size_t)p * N + (j1 << P::LOGL1) + j2] = f2torus(z[j1].x * g.inv_M);
+                out[(size_t)p * N + M + (j1 << P::LOGL1) + j2] = f2torus(z[j1].y * g.inv_M);
+            }
+        }
+        csync<C>();
+    }
+}
+
+// ------------------------------------------------------------------ host launch helpers ----
+template <typename Kern, typename... Args>
+static int launch_clustered(Kern kern, int C, int NT, size_t smem, long work_items, cudaStream_t st, Args... args) {
+    FHE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 0;
+    FHE_CUDA(cudaGetDevice(&dev));
+    FHE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    int nclusters = 0;
+    if (C > 1) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cfg.gridDim = dim3(C * (sms / C));
+        FHE_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg));
+        if (nclusters < 1) FHE_FAIL(4, "pbs: no cluster of %d CTAs with %zu B shared memory fits", C, smem);
+    } else {
+        int per_sm = 0;
+        FHE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+        if (per_sm < 1) FHE_FAIL(4, "pbs: kernel does not fit on an SM (smem %zu)", smem);
+        nclusters = per_sm * sms;
+    }
+    if ((long)nclusters > work_items) nclusters = (int)work_items;
+    cfg.gridDim = dim3((unsigned)(nclusters * C));
+    FHE_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+    return 0;
+}
+
+struct PbsLaunchArgs {
+    // common
+    PbsGeom g;
+    const double2* twT;
+    const double2* tw_mid;
+    cudaStream_t st;
+    // bootstrap
+    u64* out; const u64* in; long B; const double2* bskF; const u64* luts; const int* lut_idx;
+    // bsk conversion
+    double2* outF; const u64* bsk; long npoly;
+    // polymul
+    u64* pm_out; const i64* pm_a; const u64* pm_b;
+};
+
+template <class P>
+struct PbsPlanOps {
+    static PbsPlanMeta meta() {
+        return PbsPlanMeta{P::C, P::LOGR1, P::LRA, P::LRB, P::LRF, P::NT, P::MINB, P::KMAX, P::LOGM,
+                           (long)sizeof(double2) * P::TWN};
+    }
+    static size_t smem_pbs(const PbsGeom& g) {
+        return (size_t)(g.k + 1) * P::S * 8 + (size_t)g.J * P::BUF * 16 + (size_t)P::TWN * 16;
+    }
+    static int pbs(const PbsLaunchArgs& a) {
+        return launch_clustered(k_pbs<P>, P::C, P::NT, smem_pbs(a.g), a.B, a.st, a.out, a.in, a.B, a.bskF, a.luts,
+                                a.lut_idx, a.g, a.twT, a.tw_mid);
+    }
+    static int bsk(const PbsLaunchArgs& a) {
+        const size_t smem = (size_t)P::BUF * 16 + (size_t)P::TWN * 16;
+        return launch_clustered(k_bsk_fourier<P>, P::C, P::NT, smem, a.npoly, a.st, a.outF, a.bsk, a.npoly, a.g,
+                                a.twT, a.tw_mid);
+    }
+    static int polymul(const PbsLaunchArgs& a) {
+        const size_t smem = (size_t)2 * P::BUF * 16 + (size_t)P::TWN * 16;
+        return launch_clustered(k_polymul_test<P>, P::C, P::NT, smem, a.npoly, a.st, a.pm_out, a.pm_a, a.pm_b,
+                                a.npoly, a.g, a.twT, a.tw_mid);
+    }
+};
+
+struct PbsPlanEntry {
+    PbsPlanMeta meta;
+    int (*pbs)(const PbsLaunchArgs&);
+    int (*bsk)(const PbsLaunchArgs&);
+    int (*polymul)(const PbsLaunchArgs&);
+};
+
+#define PBS_PLAN_ENTRY(...) \
+    PbsPlanEntry { PbsPlanOps<__VA_ARGS__>::meta(), &PbsPlanOps<__VA_ARGS__>::pbs, &PbsPlanOps<__VA_ARGS__>::bsk, \
+                   &PbsPlanOps<__VA_ARGS__>::polymul }

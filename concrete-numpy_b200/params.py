@@ -36,17 +36,34 @@ def secure_log2_std(dim: int) -> float:
     return max(SECURITY_SLOPE * dim + SECURITY_BIAS, MIN_LOG2_STD)
 
 
+# (C, logM, lra, lrb, lrf, kmax) of every FFT plan instantiated in csrc/pbs_inst_{a,b,c}.cu
+_PBS_PLANS = [
+    (1, 9, 3, 0, 3, 1), (1, 8, 3, 0, 3, 1), (1, 7, 3, 0, 3, 1),
+    (1, 7, 3, 0, 2, 3), (1, 8, 3, 0, 2, 3), (1, 9, 3, 0, 2, 3), (1, 10, 4, 0, 2, 3),
+    (2, 12, 4, 4, 3, 1), (2, 11, 4, 3, 3, 1), (1, 11, 4, 0, 3, 1), (1, 10, 4, 0, 3, 1),
+    (8, 14, 4, 4, 3, 1), (8, 13, 4, 3, 3, 1), (4, 13, 4, 4, 3, 1), (4, 12, 4, 3, 3, 1),
+]
+
+
 def pbs_cluster_size(N: int, k: int, level: int) -> int:
-    """Mirror of choose_cluster() in csrc/pbs.cu (CTAs per ciphertext)."""
-    M = N // 2
-    C = 1
-    while C <= 8:
-        if M // C < 64 or M // (C * C) < 1:
-            break
-        smem = (k + 1) * (N // C) * 8 + (k + 1) * level * (M // C) * 16
-        if smem <= SMEM_MAX:
-            return C
-        C *= 2
+    """Mirror of choose_plan() in csrc/pbs.cu (CTAs per ciphertext, -1 if no on-chip layout fits)."""
+    logM = N.bit_length() - 2
+    if N != (2 << logM) or not 8 <= logM + 1 <= 15 or not 1 <= k <= 3 or not 1 <= level <= 4:
+        return -1
+    for C in (1, 2, 4, 8):
+        for (pc, plogM, lra, lrb, lrf, kmax) in _PBS_PLANS:
+            if pc != C or plogM != logM or k > kmax or (k <= 1 and kmax > 1):
+                continue
+            logL1 = lra + lrb + lrf
+            tw = 0
+            if lra:
+                tw += ((1 << lra) - 1) << (logL1 - lra)
+            if lrb:
+                tw += ((1 << lrb) - 1) << lrf
+            buf = (1 << logM) // C if C > 1 else (1 << logM)
+            smem = (k + 1) * (N // C) * 8 + (k + 1) * level * buf * 16 + tw * 16
+            if smem <= SMEM_MAX:
+                return C
     return -1
 
 
