@@ -1,6 +1,7 @@
 // Host side of the batched programmable bootstrap: plan selection, twiddle tables, C-ABI entry points.
 // The kernels live in pbs_kernels.cuh and are instantiated in pbs_inst_{a,b,c}.cu.
 #include <math.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -35,14 +36,23 @@ static size_t plan_smem(const PbsPlanMeta& m, int k, int level) {
 static int choose_plan(int N, int k, int level) {
     static const std::vector<PbsPlanEntry> plans = all_plans();
     const int logM = ilog2_exact(N) - 1;
-    for (int C = 1; C <= 8; C *= 2)
+    // experiment knob: FHE_PBS_SMALL_L=1 prefers the plans with 1024-point local transforms (twice the
+    // cluster size, two clusters resident per SM so that one's exchange phases overlap the other's math)
+    const char* e = getenv("FHE_PBS_SMALL_L");
+    const bool small_l = e && atoi(e) != 0;
+    int best = -1;
+    for (int C = 1; C <= 16; C *= 2)
         for (size_t i = 0; i < plans.size(); i++) {
             const PbsPlanMeta& m = plans[i].meta;
             if (m.C != C || m.logM != logM) continue;
             if (k > m.kmax || (k <= 1 && m.kmax > 1)) continue;
-            if (plan_smem(m, k, level) <= PBS_SMEM_MAX) return (int)i;
+            if (plan_smem(m, k, level) > PBS_SMEM_MAX) continue;
+            if (best < 0) best = (int)i;
+            else if (small_l && plans[best].meta.C * 2 == C && plan_smem(m, k, level) <= 115712 &&
+                     m.lra + m.lrb + m.lrf == 10)
+                best = (int)i;
         }
-    return -1;
+    return best;
 }
 
 struct PbsTables {
@@ -103,6 +113,10 @@ static int get_plan(int n, int k, int N, int level, int base_log, const PbsPlanE
     g.logN = logN; g.logM = logN - 1;
     g.J = (k + 1) * level;
     g.inv_M = 1.0 / (double)(N / 2);
+    {
+        const char* e = getenv("FHE_PBS_STAGGER");
+        g.stagger = e ? atoi(e) : 0;
+    }
     for (int j1 = 0; j1 < 16; j1++) {
         long double ang = M_PIl * (long double)j1 / (2.0L * R1);
         g.cj[j1] = make_double2((double)cosl(ang), (double)sinl(ang));
@@ -113,7 +127,16 @@ static int get_plan(int n, int k, int N, int level, int base_log, const PbsPlanE
     return 0;
 }
 
+static long long* g_prof_buf = nullptr;
+
 extern "C" {
+
+// development aid: device buffer of >= 16 int64 that k_pbs accumulates per-phase clock64() deltas
+// into (thread 0 of CTA 0); pass NULL to switch it off
+int fhe_pbs_set_profile(long long* dev_buf) {
+    g_prof_buf = dev_buf;
+    return 0;
+}
 
 // cluster size (CTAs per ciphertext) the on-chip layout uses for these parameters, <0 if unsupported
 int fhe_pbs_cluster_size(int N, int k, int level) {
@@ -151,7 +174,7 @@ int fhe_pbs_batch(u64* out, const u64* in, long B, const double2* bsk_f, const u
     int rc = get_plan(n, k, N, level, base_log, &e, &a);
     if (rc) return rc;
     a.st = (cudaStream_t)stream;
-    a.out = out; a.in = in; a.B = B; a.bskF = bsk_f; a.luts = luts; a.lut_idx = lut_idx;
+    a.out = out; a.in = in; a.B = B; a.bskF = bsk_f; a.luts = luts; a.lut_idx = lut_idx; a.prof = g_prof_buf;
     return e->pbs(a);
 }
 

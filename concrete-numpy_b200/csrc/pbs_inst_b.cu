@@ -1,9 +1,11 @@
-// Explicit instantiations of the bootstrap kernels: 2-CTA cluster plans and the large single-CTA plans.
+// Explicit instantiations of the bootstrap kernels: 4- and 2-CTA cluster plans and the large single-CTA plans.
 #include "pbs_kernels.cuh"
 
 static const PbsPlanEntry g_entries[] = {
-    PBS_PLAN_ENTRY(PbsPlan<2, 1, 4, 4, 3, 256, 1, 1>),   // L1 = 2048
-    PBS_PLAN_ENTRY(PbsPlan<2, 1, 4, 3, 3, 256, 1, 1>),   // L1 = 1024
+    PBS_PLAN_ENTRY(PbsPlan<4, 2, 4, 4, 3, 256, 1, 1>),   // L1 = 2048 (N = 16384)
+    PBS_PLAN_ENTRY(PbsPlan<4, 2, 4, 3, 3, 128, 2, 1>),   // L1 = 1024 (N = 8192)
+    PBS_PLAN_ENTRY(PbsPlan<2, 1, 4, 4, 3, 256, 1, 1>),   // L1 = 2048 (N = 8192)
+    PBS_PLAN_ENTRY(PbsPlan<2, 1, 4, 3, 3, 128, 2, 1>),   // L1 = 1024 (N = 4096)
     PBS_PLAN_ENTRY(PbsPlan<1, 4, 4, 0, 3, 256, 1, 1>),   // M = 2048 (N = 4096)
     PBS_PLAN_ENTRY(PbsPlan<1, 3, 4, 0, 3, 128, 3, 1>),   // M = 1024 (N = 2048)
 };

@@ -36,13 +36,14 @@ struct PbsGeom {
     int logN, logM;
     int J;                // (k+1)*level forward transforms per CMUX
     double inv_M;
+    int stagger;          // start-up delay per cluster id (SM cycles), de-synchronises the clusters' phases
     double2 cj[16];       // exp(i*pi*j1/(2*R1)), j1 < R1
 };
 
 // Compile-time FFT plan.  M = R1 * L1, L1 = RA * RB * RF (RA / RB = 1 when absent).
 template <int C_, int LOGR1_, int LRA_, int LRB_, int LRF_, int NT_, int MINB_, int KMAX_>
 struct PbsPlan {
-    static constexpr int C = C_, LOGC = (C_ == 1 ? 0 : C_ == 2 ? 1 : C_ == 4 ? 2 : 3);
+    static constexpr int C = C_, LOGC = (C_ == 1 ? 0 : C_ == 2 ? 1 : C_ == 4 ? 2 : C_ == 8 ? 3 : 4);
     static constexpr int LOGR1 = LOGR1_, R1 = 1 << LOGR1_;
     static constexpr int LRA = LRA_, LRB = LRB_, LRF = LRF_, RF = 1 << LRF_;
     static constexpr int NT = NT_, MINB = MINB_, KMAX = KMAX_;
@@ -312,15 +313,89 @@ __device__ __forceinline__ size_t ggsw_slice(int j, int o, int k, int rank) {
     return (((size_t)(j * (k + 1) + o) * P::C + rank) << P::LOGBUF);
 }
 
+// ---- P1 of a CMUX for every item (c, q) of this CTA: diff = X^a * ACC - ACC, signed decomposition
+// (closest representable, balanced digits), one stage-1 emit per level.  ST = u32 when the kept
+// level*base_log bits fit 31 bits (halves the registers of the decomposition state).
+template <class P, typename ST>
+__device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* __restrict__ work, int rank, int a,
+                                         const PbsGeom& g, const double2* __restrict__ twT) {
+    constexpr int C = P::C, R1 = P::R1, NT = P::NT, Q = P::Q, N = P::N;
+    const int k = g.k, level = g.level, base_log = g.base_log;
+    const ST mask = (ST)((1ULL << base_log) - 1);
+    const int nonrep = 64 - level * base_log;
+#pragma unroll 1
+    for (int it = threadIdx.x; it < ((k + 1) << P::LOGQ); it += NT) {
+        const int c = it >> P::LOGQ, q = it & (Q - 1);
+        const int j2 = (rank << P::LOGQ) + q;
+        const u64* accc = acc + ((size_t)c << P::LOGS);
+        ST st[2 * R1];
+        {
+            const int base = (j2 - a) & (2 * N - 1);
+#pragma unroll
+            for (int half = 0; half < 2; half++) {       // two batches bound the registers in flight
+                u64 rv[R1];
+                unsigned negm = 0;
+#pragma unroll
+                for (int e = 0; e < R1; e++) {
+                    const int hj = half * R1 + e;
+                    const int v = (base + (hj << P::LOGL1)) & (2 * N - 1);
+                    const int idx = v & (N - 1);
+                    negm |= (unsigned)(v >> (P::LOGM + 1)) << e;
+                    const int jj2 = idx & (P::L1 - 1);
+                    const int slot = ((idx >> P::LOGL1) << P::LOGQ) + (jj2 & (Q - 1));
+                    rv[e] = *peer<C>(accc + slot, jj2 >> P::LOGQ);
+                }
+#pragma unroll
+                for (int e = 0; e < R1; e++) {
+                    const int hj = half * R1 + e;
+                    const u64 own = accc[(hj << P::LOGQ) + q];
+                    const u64 diff = (((negm >> e) & 1) ? (0ULL - rv[e]) : rv[e]) - own;
+                    st[hj] = (ST)(((diff >> (nonrep - 1)) + 1) >> 1);      // closest representable
+                }
+            }
+        }
+        double2 T[R1];
+        load_T<P>(T, twT, j2);
+#pragma unroll 1
+        for (int t = 0; t < level; t++) {
+            const int lv = level - 1 - t;       // digits come out least significant level first
+            double re[R1], im[R1];
+#pragma unroll
+            for (int hj = 0; hj < 2 * R1; hj++) {
+                const ST res = st[hj] & mask;
+                const ST s2 = st[hj] >> base_log;
+                const ST carry = (((res - 1) | s2) & res) >> (base_log - 1);
+                st[hj] = s2 + carry;
+                double d;
+                if (sizeof(ST) == 4) d = (double)((int)res - (int)(carry << base_log));
+                else d = (double)((i64)res - (i64)((u64)carry << base_log));
+                if (hj < R1) re[hj] = d;
+                else im[hj - R1] = d;
+            }
+            stage1_emit<P>(work + ((size_t)(c * level + lv) << P::LOGBUF), j2, re, im, T, g);
+        }
+    }
+}
+
 // ---- the bootstrap kernel ------------------------------------------------------------------
 template <class P>
 __global__ void __launch_bounds__(P::NT, P::MINB)
 k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* __restrict__ bskF,
       const u64* __restrict__ luts, const int* __restrict__ lut_idx, const PbsGeom g,
-      const double2* __restrict__ twT, const double2* __restrict__ tw_mid) {
+      const double2* __restrict__ twT, const double2* __restrict__ tw_mid, long long* prof) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int C = P::C, R1 = P::R1, NT = P::NT, RF = P::RF, BUF = P::BUF, Q = P::Q, S = P::S;
     constexpr int N = P::N, M = P::M;
+    // optional phase timing (development aid, fhe_pbs_set_profile): thread 0 of CTA 0 accumulates
+    // clock64() deltas per phase
+    const bool do_prof = (prof != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
+    long long t_last = do_prof ? clock64() : 0;
+#define PBS_PROF(slot)                         \
+    if (do_prof) {                             \
+        const long long t_now = clock64();     \
+        prof[slot] += t_now - t_last;          \
+        t_last = t_now;                        \
+    }
     constexpr int NG = BUF / RF;                    // butterfly groups of the fused pass
     const int k = g.k, level = g.level, J = g.J, base_log = g.base_log;
     u64* acc = reinterpret_cast<u64*>(smem_raw);                                   // [(k+1)][S]
@@ -331,10 +406,14 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
     if (C > 1) rank = (int)cg::this_cluster().block_rank();
     const long cluster_id = blockIdx.x / C, nclusters = gridDim.x / C;
     const size_t ggsw_stride = (size_t)J * (k + 1) * C * BUF;   // double2 per CMUX iteration
-    const u64 mask = (1ULL << base_log) - 1;
-    const int nonrep = 64 - level * base_log;
 
     for (int t = tid; t < P::TWN; t += NT) tw_s[t] = tw_mid[t];
+    if (g.stagger > 0) {
+        // all clusters run the same phase sequence; started together they would hit the L2 (GGSW
+        // streaming) and the SM-to-SM network (stage-1 scatter) at the same instants
+        const long long t_end = clock64() + (long long)(cluster_id % 64) * g.stagger;
+        while (clock64() < t_end) __nanosleep(100);
+    }
 
     for (long ct = cluster_id; ct < B; ct += nclusters) {
         const u64* lwe = in + (size_t)ct * (g.n + 1);
@@ -356,54 +435,16 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
             const int a = a_next;
             a_next = (i + 1 < g.n) ? modswitch(lwe[i + 1], g.logN) : 0;
             // ---- P1: rotate, subtract, decompose, fold+twist, radix-R1 stage, scatter to owners
-#pragma unroll 1
-            for (int it = tid; it < ((k + 1) << P::LOGQ); it += NT) {
-                const int c = it >> P::LOGQ, q = it & (Q - 1);
-                const int j2 = (rank << P::LOGQ) + q;
-                const u64* accc = acc + ((size_t)c << P::LOGS);
-                double2 T[R1];
-                load_T<P>(T, twT, j2);
-                u64 st[2 * R1];
-                {
-                    const int base = (j2 - a) & (2 * N - 1);
-                    u64 rv[2 * R1];
-                    unsigned negm = 0;
-#pragma unroll
-                    for (int hj = 0; hj < 2 * R1; hj++) {
-                        const int v = (base + (hj << P::LOGL1)) & (2 * N - 1);
-                        const int idx = v & (N - 1);
-                        negm |= (unsigned)(v >> (P::LOGM + 1)) << hj;
-                        const int jj2 = idx & (P::L1 - 1);
-                        const int slot = ((idx >> P::LOGL1) << P::LOGQ) + (jj2 & (Q - 1));
-                        rv[hj] = *peer<C>(accc + slot, jj2 >> P::LOGQ);
-                    }
-#pragma unroll
-                    for (int hj = 0; hj < 2 * R1; hj++) {
-                        const u64 own = accc[(hj << P::LOGQ) + q];
-                        const u64 diff = (((negm >> hj) & 1) ? (0ULL - rv[hj]) : rv[hj]) - own;
-                        st[hj] = ((diff >> (nonrep - 1)) + 1) >> 1;      // closest representable
-                    }
-                }
-#pragma unroll 1
-                for (int t = 0; t < level; t++) {
-                    const int lv = level - 1 - t;       // digits come out least significant level first
-                    double re[R1], im[R1];
-#pragma unroll
-                    for (int hj = 0; hj < 2 * R1; hj++) {
-                        u64 res = st[hj] & mask;
-                        u64 s2 = st[hj] >> base_log;
-                        u64 carry = (((res - 1) | s2) & res) >> (base_log - 1);
-                        st[hj] = s2 + carry;
-                        const double d = (double)((i64)res - (i64)(carry << base_log));
-                        if (hj < R1) re[hj] = d;
-                        else im[hj - R1] = d;
-                    }
-                    stage1_emit<P>(work + ((size_t)(c * level + lv) << P::LOGBUF), j2, re, im, T, g);
-                }
-            }
+            if (level * base_log <= 31)
+                p1_items<P, unsigned>(acc, work, rank, a, g, twT);
+            else
+                p1_items<P, u64>(acc, work, rank, a, g, twT);
+            PBS_PROF(0)
             csync<C>();
+            PBS_PROF(1)
             // ---- P2: mid passes of all J buffers
             mid_passes<P, false>(work, J, tw_s);
+            PBS_PROF(2)
             // ---- P3: last forward pass + multiply-accumulate against GGSW_i + first inverse pass
             {
                 const double2* gg = bskF + (size_t)i * ggsw_stride;
@@ -414,41 +455,39 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
                     for (int o = 0; o <= P::KMAX; o++)
 #pragma unroll
                         for (int m = 0; m < RF; m++) r[o][m] = make_double2(0.0, 0.0);
-                    double2 gA[P::KMAX + 1][RF], gB[P::KMAX + 1][RF];
-                    auto load_g = [&](double2(&dst)[P::KMAX + 1][RF], int j) {
+                    // rolling prefetch: every GGSW register is re-loaded for the next input polynomial right
+                    // after its last use, so (k+1)*RF 16-byte loads stay in flight behind the FMAs
+                    double2 gv[P::KMAX + 1][RF];
+                    const double2* gp = gg + ((size_t)rank << P::LOGBUF) + w;
+                    const size_t o_stride = (size_t)P::C << P::LOGBUF;
 #pragma unroll
-                        for (int o = 0; o <= P::KMAX; o++)
-                            if (o <= k) {
-                                const double2* p = gg + ggsw_slice<P>(j, o, k, rank) + w;
+                    for (int o = 0; o <= P::KMAX; o++)
+                        if (o <= k) {
 #pragma unroll
-                                for (int m = 0; m < RF; m++) dst[o][m] = __ldg(p + m * NG);
-                            }
-                    };
-                    auto mac = [&](const double2(&gv)[P::KMAX + 1][RF], int j) {
+                            for (int m = 0; m < RF; m++) gv[o][m] = __ldg(gp + o * o_stride + m * NG);
+                        }
+#pragma unroll 1
+                    for (int j = 0; j < J; j++) {
                         double2 x[RF];
                         const double2* base = work + ((size_t)j << P::LOGBUF);
 #pragma unroll
                         for (int m = 0; m < RF; m++) x[m] = base[SW(w * RF + m)];
                         Dft<RF, false>::run(x);
+                        const double2* gn = gp + (size_t)(j + 1) * (k + 1) * o_stride;
+                        const bool more = (j + 1 < J);
 #pragma unroll
                         for (int o = 0; o <= P::KMAX; o++)
                             if (o <= k) {
 #pragma unroll
                                 for (int m = 0; m < RF; m++) {
-                                    r[o][m].x = fma(x[m].x, gv[o][m].x, r[o][m].x);
-                                    r[o][m].x = fma(-x[m].y, gv[o][m].y, r[o][m].x);
-                                    r[o][m].y = fma(x[m].x, gv[o][m].y, r[o][m].y);
-                                    r[o][m].y = fma(x[m].y, gv[o][m].x, r[o][m].y);
+                                    const double2 b = gv[o][m];
+                                    r[o][m].x = fma(x[m].x, b.x, r[o][m].x);
+                                    r[o][m].x = fma(-x[m].y, b.y, r[o][m].x);
+                                    r[o][m].y = fma(x[m].x, b.y, r[o][m].y);
+                                    r[o][m].y = fma(x[m].y, b.x, r[o][m].y);
+                                    if (more) gv[o][m] = __ldg(gn + o * o_stride + m * NG);
                                 }
                             }
-                    };
-                    load_g(gA, 0);
-#pragma unroll 1
-                    for (int j = 0; j < J; j += 2) {
-                        if (j + 1 < J) load_g(gB, j + 1);
-                        mac(gA, j);
-                        if (j + 2 < J) load_g(gA, j + 2);
-                        if (j + 1 < J) mac(gB, j + 1);
                     }
 #pragma unroll
                     for (int o = 0; o <= P::KMAX; o++)
@@ -461,9 +500,12 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
                 }
             }
             __syncthreads();
+            PBS_PROF(3)
             // ---- P4: inverse mid passes of the k+1 output buffers
             mid_passes<P, true>(work, k + 1, tw_s);
+            PBS_PROF(4)
             if (C > 1) csync<C>();
+            PBS_PROF(5)
             // ---- P5: gather from owners, inverse radix-R1 stage, untwist, round, ACC +=
 #pragma unroll 1
             for (int it = tid; it < ((k + 1) << P::LOGQ); it += NT) {
@@ -480,7 +522,9 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
                     acco[((R1 + j1) << P::LOGQ) + q] += f2torus(z[j1].y * g.inv_M);
                 }
             }
+            PBS_PROF(6)
             csync<C>();
+            PBS_PROF(7)
         }
         // ---- sample extract coefficient 0
         {
@@ -497,7 +541,9 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
             }
         }
         // the same thread re-initialises the same ACC words at the top of the loop
+        PBS_PROF(8)
     }
+#undef PBS_PROF
 }
 
 // forward transform of one polynomial held as folded (re, im) inputs by the caller's functor:
@@ -635,6 +681,7 @@ static int launch_clustered(Kern kern, int C, int NT, size_t smem, long work_ite
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     int nclusters = 0;
+    if (C > 8) FHE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     if (C > 1) {
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = C;
@@ -664,7 +711,7 @@ struct PbsLaunchArgs {
     const double2* tw_mid;
     cudaStream_t st;
     // bootstrap
-    u64* out; const u64* in; long B; const double2* bskF; const u64* luts; const int* lut_idx;
+    u64* out; const u64* in; long B; const double2* bskF; const u64* luts; const int* lut_idx; long long* prof;
     // bsk conversion
     double2* outF; const u64* bsk; long npoly;
     // polymul
@@ -682,7 +729,7 @@ struct PbsPlanOps {
     }
     static int pbs(const PbsLaunchArgs& a) {
         return launch_clustered(k_pbs<P>, P::C, P::NT, smem_pbs(a.g), a.B, a.st, a.out, a.in, a.B, a.bskF, a.luts,
-                                a.lut_idx, a.g, a.twT, a.tw_mid);
+                                a.lut_idx, a.g, a.twT, a.tw_mid, a.prof);
     }
     static int bsk(const PbsLaunchArgs& a) {
         const size_t smem = (size_t)P::BUF * 16 + (size_t)P::TWN * 16;

@@ -75,6 +75,10 @@ int fhe_pbs_batch(uint64_t* out /* [B][kN+1] */, const uint64_t* in /* [B][n+1] 
                   const int* lut_idx /* [B] or NULL */, int n, int k, int N, int level, int base_log,
                   void* stream);
 
+/* development aid: k_pbs accumulates per-phase clock64() deltas of one CTA into dev_buf[0..15]
+ * (NULL switches it off); not part of the reference-facing surface */
+int fhe_pbs_set_profile(long long* dev_buf);
+
 /* ---- torus linear algebra on [E][L] tensors (L = kN+1) --------------------------------
  * ia / ib: optional int32 row maps (numpy broadcasting resolved by the host), NULL = identity.
  * FHE.add_eint / FHELinalg.add_eint (node_converter.py:216-242) ... */

@@ -1,0 +1,39 @@
+"""Development aid: per-phase cycle breakdown of k_pbs (one CTA) for a parameter set."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from concrete_numpy_b200 import engine as E, _lib
+from concrete_numpy_b200.params import REFERENCE_SETS
+
+dev = torch.device("cuda:0")
+NAMES = ["P1 decomp+stage1", "sync A", "mid fwd", "fused MAC", "mid inv", "sync B", "P5 gather+acc", "sync C", "extract+init"]
+for pbits, B in ((8, 36), (6, 148), (4, 888)):
+    p = REFERENCE_SETS[pbits]
+    if len(sys.argv) > 1 and str(pbits) not in sys.argv[1:]:
+        continue
+    ks = E.KeySet(p, dev, seed=1)
+    ev = E.EvalKeys.of(ks)
+    rng = np.random.default_rng(0)
+    m = rng.integers(0, 1 << p.p, B).astype(np.uint64)
+    table = rng.integers(0, 1 << p.p, (1, 1 << p.p))
+    luts = E.from_np_u64(E.build_lut_accumulators(p, table), dev)
+    small = E.keyswitch(ev, E.encrypt(ks, m))
+    E.bootstrap(ev, small, luts, None)
+    prof = torch.zeros(16, dtype=torch.int64, device=dev)
+    _lib.call("fhe_pbs_set_profile", prof.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = E.bootstrap(ev, small, luts, None)
+    e1.record()
+    torch.cuda.synchronize()
+    _lib.call("fhe_pbs_set_profile", None)
+    ok = bool(np.array_equal(E.decrypt(ks, out), table[0, m.astype(np.int64)].astype(np.uint64)))
+    c = prof.cpu().numpy()[:9].astype(np.float64)
+    ms = e0.elapsed_time(e1)
+    ncmux = c.sum() / (ms * 1e-3 * 1.9e9) and None
+    print(f"p={pbits} N={p.N} n={p.n} B={B} ok={ok} kernel {ms:.2f} ms; CTA0 total {c.sum()/1e6:.2f} Mcycles "
+          f"=> {c.sum() / (ms * 1e-3) / 1e6:.0f} MHz")
+    for nm, v in zip(NAMES, c):
+        print(f"   {nm:18s} {v / max(c.sum(), 1) * 100:5.1f}%   {v / 1e3:10.0f} kcycles")
+    del ks, ev
+    torch.cuda.empty_cache()
