@@ -116,6 +116,8 @@ static int get_plan(int n, int k, int N, int level, int base_log, const PbsPlanE
     {
         const char* e = getenv("FHE_PBS_STAGGER");
         g.stagger = e ? atoi(e) : 0;
+        e = getenv("FHE_PBS_DBG");
+        g.dbg = e ? atoi(e) : 0;
     }
     for (int j1 = 0; j1 < 16; j1++) {
         long double ang = M_PIl * (long double)j1 / (2.0L * R1);

@@ -36,6 +36,7 @@ struct PbsGeom {
     int logN, logM;
     int J;                // (k+1)*level forward transforms per CMUX
     double inv_M;
+    int dbg;              // development ablation bits (FHE_PBS_DBG), 0 in production
     int stagger;          // start-up delay per cluster id (SM cycles), de-synchronises the clusters' phases
     double2 cj[16];       // exp(i*pi*j1/(2*R1)), j1 < R1
 };
@@ -181,7 +182,50 @@ __device__ __forceinline__ T* peer(T* p, int rank) {
     return cg::this_cluster().map_shared_rank(p, rank);
 }
 
+// explicit distributed-shared-memory accesses (32-bit shared::cluster addresses, no generic LD/ST)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, int rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ u64 ld_cluster_u64(unsigned addr) {
+    u64 v;
+    asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 ld_cluster_f64x2(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_cluster_f64x2(unsigned addr, double2 v) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+// L2 prefetch of a contiguous global range (bytes multiple of 16)
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// int32 -> double and double -> torus without the slow conversion unit (I2F / FRND / F2I.S64):
+// magic-number arithmetic on the FP64 pipe.
+__device__ __forceinline__ double i32_to_f64(int d) {
+    return __hiloint2double(0x43300000, d ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
+}
 __device__ __forceinline__ u64 f2torus(double x) {
+    const double MAGIC = 6755399441055744.0;                        // 1.5 * 2^52
+    const double r = (x * 5.42101086242752217e-20 + MAGIC) - MAGIC; // rint(x / 2^64), |x| < 2^115
+    x = fma(-18446744073709551616.0, r, x);                         // exact: x in [-2^63, 2^63], an integer
+    const double hs = fma(x, 2.3283064365386963e-10, MAGIC);        // x / 2^32 rounded to an integer (+ MAGIC)
+    const int hi = __double2loint(hs);
+    const double lo_d = fma(-4294967296.0, hs - MAGIC, x);          // exact, |lo| <= 2^31
+    const int lo = __double2loint(lo_d + MAGIC);
+    u64 res = ((u64)(unsigned)hi << 32) + (u64)(i64)lo;
+    if (lo_d >= 2147483648.0) res += 1ULL << 32;                    // lo == +2^31 wrapped to -2^31
+    return res;
+}
+__device__ __forceinline__ u64 f2torus_ref(double x) {
+
     x -= 18446744073709551616.0 * rint(x * 5.42101086242752217e-20);
     return (u64)__double2ll_rn(x);
 }
@@ -268,10 +312,11 @@ __device__ __forceinline__ void stage1_emit(double2* dst_buf, int j2, const doub
         z[j1] = (j1 == 0) ? d : cmul(d, g.cj[j1]);
     }
     Dft<P::R1, false>::run(z);
+    const unsigned a0 = smem_u32(dst_buf + SW(j2));
 #pragma unroll
     for (int t1 = 0; t1 < P::R1; t1++) {
         const double2 v = cmul(z[t1], T[t1]);
-        if (P::C > 1) *peer<P::C>(dst_buf + SW(j2), t1) = v;
+        if (P::C > 1) st_cluster_f64x2(mapa_u32(a0, (g.dbg & 4) ? (int)cg::this_cluster().block_rank() : t1), v);
         else dst_buf[SW((t1 << P::LOGL1) + j2)] = v;
     }
 }
@@ -281,9 +326,10 @@ template <class P>
 __device__ __forceinline__ void stage1_gather(const double2* src_buf, int j2, const double2* T, const PbsGeom& g,
                                               double2* z /* [R1]: (coef j1*L1+j2, coef M+j1*L1+j2), unnormalised */) {
     double2 v[P::R1];
+    const unsigned a0 = smem_u32(src_buf + SW(j2));
 #pragma unroll
     for (int t1 = 0; t1 < P::R1; t1++) {
-        if (P::C > 1) v[t1] = *peer<P::C>(src_buf + SW(j2), t1);
+        if (P::C > 1) v[t1] = ld_cluster_f64x2(mapa_u32(a0, (g.dbg & 8) ? (int)cg::this_cluster().block_rank() : t1));
         else v[t1] = src_buf[SW((t1 << P::LOGL1) + j2)];
     }
 #pragma unroll
@@ -315,7 +361,7 @@ __device__ __forceinline__ size_t ggsw_slice(int j, int o, int k, int rank) {
 
 // ---- P1 of a CMUX for every item (c, q) of this CTA: diff = X^a * ACC - ACC, signed decomposition
 // (closest representable, balanced digits), one stage-1 emit per level.  ST = u32 when the kept
-// level*base_log bits fit 31 bits (halves the registers of the decomposition state).
+// level*base_log bits fit 30 bits (halves the registers of the decomposition state).
 template <class P, typename ST>
 __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* __restrict__ work, int rank, int a,
                                          const PbsGeom& g, const double2* __restrict__ twT) {
@@ -328,34 +374,43 @@ __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* _
         const int c = it >> P::LOGQ, q = it & (Q - 1);
         const int j2 = (rank << P::LOGQ) + q;
         const u64* accc = acc + ((size_t)c << P::LOGS);
+        double2 T[R1];
+        load_T<P>(T, twT, j2);                  // L2 latency hides behind the rotated (remote) loads
         ST st[2 * R1];
         {
+            // coefficient hj*L1 + j2 of X^a * ACC is +-ACC[(hj*L1 + j2 - a) mod 2N]: the low bits (owner CTA
+            // and slot offset) are the same for all hj of the item, only the block index hb + hj moves
             const int base = (j2 - a) & (2 * N - 1);
+            const int jj2 = base & (P::L1 - 1);
+            const int hb = base >> P::LOGL1;                      // in [0, 4*R1)
+            const int owner = (g.dbg & 2) ? rank : (jj2 >> P::LOGQ);
+            const u64* src_local = accc + (jj2 & (Q - 1));
+            const unsigned src_peer = (C > 1) ? mapa_u32(smem_u32(src_local), owner) : 0u;
 #pragma unroll
             for (int half = 0; half < 2; half++) {       // two batches bound the registers in flight
                 u64 rv[R1];
-                unsigned negm = 0;
 #pragma unroll
                 for (int e = 0; e < R1; e++) {
-                    const int hj = half * R1 + e;
-                    const int v = (base + (hj << P::LOGL1)) & (2 * N - 1);
-                    const int idx = v & (N - 1);
-                    negm |= (unsigned)(v >> (P::LOGM + 1)) << e;
-                    const int jj2 = idx & (P::L1 - 1);
-                    const int slot = ((idx >> P::LOGL1) << P::LOGQ) + (jj2 & (Q - 1));
-                    rv[e] = *peer<C>(accc + slot, jj2 >> P::LOGQ);
+                    const int hjp = (hb + half * R1 + e) & (2 * R1 - 1);
+                    if (C > 1) rv[e] = ld_cluster_u64(src_peer + ((unsigned)hjp << (P::LOGQ + 3)));
+                    else rv[e] = src_local[hjp << P::LOGQ];
                 }
 #pragma unroll
                 for (int e = 0; e < R1; e++) {
                     const int hj = half * R1 + e;
+                    const int hjr = (hb + hj) & (4 * R1 - 1);
                     const u64 own = accc[(hj << P::LOGQ) + q];
-                    const u64 diff = (((negm >> e) & 1) ? (0ULL - rv[e]) : rv[e]) - own;
-                    st[hj] = (ST)(((diff >> (nonrep - 1)) + 1) >> 1);      // closest representable
+                    const u64 diff = ((hjr >> (P::LOGR1 + 1)) ? (0ULL - rv[e]) : rv[e]) - own;
+                    if (sizeof(ST) == 4) {
+                        // level*base_log <= 30: the state only needs bits [nonrep-1, 64) of diff
+                        const unsigned top = (unsigned)(diff >> 32);
+                        const unsigned sh = (unsigned)(nonrep - 33);
+                        st[hj] = (ST)(((top >> sh) + 1u) >> 1);
+                    } else
+                        st[hj] = (ST)(((diff >> (nonrep - 1)) + 1) >> 1);      // closest representable
                 }
             }
         }
-        double2 T[R1];
-        load_T<P>(T, twT, j2);
 #pragma unroll 1
         for (int t = 0; t < level; t++) {
             const int lv = level - 1 - t;       // digits come out least significant level first
@@ -367,7 +422,7 @@ __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* _
                 const ST carry = (((res - 1) | s2) & res) >> (base_log - 1);
                 st[hj] = s2 + carry;
                 double d;
-                if (sizeof(ST) == 4) d = (double)((int)res - (int)(carry << base_log));
+                if (sizeof(ST) == 4) d = i32_to_f64((int)res - (int)(carry << base_log));
                 else d = (double)((i64)res - (i64)((u64)carry << base_log));
                 if (hj < R1) re[hj] = d;
                 else im[hj - R1] = d;
@@ -434,8 +489,12 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
         for (int i = 0; i < g.n; i++) {
             const int a = a_next;
             a_next = (i + 1 < g.n) ? modswitch(lwe[i + 1], g.logN) : 0;
+            // GGSW_{i+1} slices of this rank -> L2 one iteration ahead (HBM latency off the MAC's path)
+            if (i + 1 < g.n && tid < J * (k + 1) && !(g.dbg & 16))
+                prefetch_l2_bulk(bskF + (size_t)(i + 1) * ggsw_stride + (((size_t)tid * C + rank) << P::LOGBUF),
+                                 (unsigned)(sizeof(double2) << P::LOGBUF));
             // ---- P1: rotate, subtract, decompose, fold+twist, radix-R1 stage, scatter to owners
-            if (level * base_log <= 31)
+            if (level * base_log <= 30)
                 p1_items<P, unsigned>(acc, work, rank, a, g, twT);
             else
                 p1_items<P, u64>(acc, work, rank, a, g, twT);
@@ -464,7 +523,7 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
                     for (int o = 0; o <= P::KMAX; o++)
                         if (o <= k) {
 #pragma unroll
-                            for (int m = 0; m < RF; m++) gv[o][m] = __ldg(gp + o * o_stride + m * NG);
+                            for (int m = 0; m < RF; m++) gv[o][m] = (g.dbg & 1) ? make_double2(1.0, 0.5) : __ldg(gp + o * o_stride + m * NG);
                         }
 #pragma unroll 1
                     for (int j = 0; j < J; j++) {
@@ -485,7 +544,7 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
                                     r[o][m].x = fma(-x[m].y, b.y, r[o][m].x);
                                     r[o][m].y = fma(x[m].x, b.y, r[o][m].y);
                                     r[o][m].y = fma(x[m].y, b.x, r[o][m].y);
-                                    if (more) gv[o][m] = __ldg(gn + o * o_stride + m * NG);
+                                    if (more && !(g.dbg & 1)) gv[o][m] = __ldg(gn + o * o_stride + m * NG);
                                 }
                             }
                     }
