@@ -27,6 +27,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "tmem.cuh"
 namespace cg = cooperative_groups;
 
 #define PBS_SMEM_MAX 232448  // 227 KB opt-in dynamic shared memory per CTA on sm_100
@@ -57,14 +58,28 @@ struct PbsPlan {
     static constexpr int SB = 1 << LRF_;                  // stride of mid pass B (sub-length L1 / RA)
     static constexpr int TWA = LRA_ ? ((1 << LRA_) - 1) * SA : 0;
     static constexpr int TWB = LRB_ ? ((1 << LRB_) - 1) * SB : 0;
-    static constexpr int TWN = TWA + TWB;                 // shared twiddle entries
+    static constexpr int TWN = TWA + TWB;                 // entries of the twiddle table of the mid passes
+    static constexpr int TW_SMEM = (MINB_ == 1) ? 0 : TWA + TWB;   // ... held in shared memory unless TMEM_TW
+    // Tensor-memory columns per thread: the R-1 twiddles of the thread's (fixed) butterfly index in each mid
+    // pass and the R1 stage-1 twiddles of each of its NQ item columns, padded to tcgen05 ld/st sizes
+    static constexpr int tm_pad(int words) { return words <= 4 ? 4 : words <= 8 ? 8 : words <= 16 ? 16 : words <= 32 ? 32 : 64; }
+    static constexpr int TM_A = LRA_ ? tm_pad(4 * ((1 << LRA_) - 1)) : 0;
+    static constexpr int TM_B = LRB_ ? tm_pad(4 * ((1 << LRB_) - 1)) : 0;
+    // Measured (profiles/r01_ubench_tmem.log + A/B runs): tcgen05.ld costs ~75 cycles when the memory pipe is
+    // quiet but queues behind outstanding global / remote accesses of the SM, so tensor memory holds only the
+    // mid-pass twiddles and only in the plans that run one CTA per SM; the others keep them in shared memory.
+    static constexpr bool TMEM_TW = (MINB_ == 1);
+    static constexpr int TM_THREAD = TM_A + TM_B;
+    static constexpr int TM_NEED = (TM_THREAD > 0 ? TM_THREAD : 1) * ((NT_ + 127) / 128);
+    static constexpr int TM_CTA = TM_NEED <= 32 ? 32 : TM_NEED <= 64 ? 64 : TM_NEED <= 128 ? 128 : TM_NEED <= 256 ? 256 : 512;
+    static_assert(TM_NEED <= 512, "tensor memory holds 512 columns");
     static_assert(C_ == 1 || LOGR1_ == LOGC, "cluster plans use R1 == C");
     static_assert(LRA_ > 0 || LRB_ == 0, "pass B requires pass A");
 };
 
 struct PbsPlanMeta {       // what the host needs to know about a plan
     int C, logR1, lra, lrb, lrf, NT, minb, kmax, logM;
-    long smem_fixed;       // twiddle bytes
+    long smem_fixed;       // bytes of shared memory besides ACC and the work buffers (twiddles live in TMEM)
 };
 
 // ---- small complex helpers -----------------------------------------------------------
@@ -235,11 +250,72 @@ __device__ __forceinline__ int modswitch(u64 x, int logN) {  // -> Z_{2N}
     return (int)(t & ((1ULL << lg) - 1));
 }
 
+// ---- per-thread twiddle factors in tensor memory -------------------------------------------------
+struct TwCtx {
+    unsigned base;            // tensor-memory allocation base (for dealloc)
+    unsigned tA, tB;          // this thread's mid-pass twiddles in tensor memory (TMEM_TW plans)
+    const double2 *sA, *sB;   // mid-pass twiddle tables in shared memory (other plans)
+    const double2* twT;       // stage-1 twiddles [R1][L1] in global memory (L1/L2 resident)
+};
+
+// twiddles of one mid pass for this thread's butterfly index, from the global table [(R-1)][S]
+template <int LR, int LOGLC, int LOGBUF, int NT>
+__device__ __forceinline__ void tw_init_pass(unsigned taddr, const double2* __restrict__ tw_g) {
+    constexpr int R = 1 << LR;
+    constexpr int LOGSS = LOGLC - LR, SS = 1 << LOGSS;
+    constexpr int NBF = 1 << (LOGBUF - LR);
+    constexpr int TMW = (4 * (R - 1) <= 4) ? 4 : (4 * (R - 1) <= 16) ? 16 : (4 * (R - 1) <= 32) ? 32 : 64;
+    const int w = (NBF >= NT) ? (int)threadIdx.x : (int)(threadIdx.x % NBF);
+    const int q = w & (SS - 1);
+    double2 t[TMW / 4];
+#pragma unroll
+    for (int m = 1; m <= TMW / 4; m++) t[m - 1] = (m < R) ? tw_g[((m - 1) << LOGSS) + q] : make_double2(0.0, 0.0);
+    tmem_store_c<TMW / 4>(taddr, t);
+}
+
+// twiddle set-up: tensor-memory allocation + fill (TMEM_TW plans) or shared-memory tables; all threads call it
+template <class P>
+__device__ __forceinline__ TwCtx tw_setup(double2* tw_smem, const double2* __restrict__ twT,
+                                          const double2* __restrict__ tw_mid) {
+    TwCtx tw;
+    tw.twT = twT;
+    tw.sA = tw_smem;
+    tw.sB = tw_smem + P::TWA;
+    tw.base = tw.tA = tw.tB = 0;
+    if constexpr (P::TMEM_TW) {
+        __shared__ unsigned s_tmem_base;
+        const int warp = threadIdx.x >> 5;
+        if (warp == 0) tmem_alloc(&s_tmem_base, P::TM_CTA);
+        tmem_fence_before_sync();
+        __syncthreads();
+        tmem_fence_after_sync();
+        tw.base = s_tmem_base;
+        const unsigned mine = tw.base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)((warp >> 2) * P::TM_THREAD);
+        tw.tA = mine;
+        tw.tB = mine + P::TM_A;
+        if constexpr (P::LRA > 0) tw_init_pass<P::LRA, P::LOGL1, P::LOGBUF, P::NT>(tw.tA, tw_mid);
+        if constexpr (P::LRB > 0) tw_init_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, P::NT>(tw.tB, tw_mid + P::TWA);
+        tmem_wait_st();
+    } else {
+        for (int t = threadIdx.x; t < P::TWN; t += P::NT) tw_smem[t] = tw_mid[t];
+        __syncthreads();
+    }
+    return tw;
+}
+template <class P>
+__device__ __forceinline__ void tw_teardown(const TwCtx& tw) {
+    if constexpr (P::TMEM_TW) {
+        tmem_fence_before_sync();
+        __syncthreads();
+        if ((threadIdx.x >> 5) == 0) tmem_dealloc(tw.base, P::TM_CTA);
+    }
+}
+
 // ---- one mid pass over `nbuf` buffers of BUF points, sub-transform length 2^LOGLC ------------
 // forward (DIF): y_m = DFT_R(x)_m * W_Lc^{q m};   inverse (DIT): mirror with conjugates.
 // A thread keeps the R-1 twiddles of its butterfly index in registers across the buffers it handles.
-template <int LR, int LOGLC, int LOGBUF, int NT, bool INV>
-__device__ __forceinline__ void mid_pass(double2* __restrict__ work, int nbuf,
+template <int LR, int LOGLC, int LOGBUF, int NT, bool INV, bool TM>
+__device__ __forceinline__ void mid_pass(double2* __restrict__ work, int nbuf, unsigned tw_taddr /* TMEM */,
                                          const double2* __restrict__ tw /* shared: [(R-1)][S] */) {
     constexpr int R = 1 << LR;
     constexpr int LOGSS = LOGLC - LR, SS = 1 << LOGSS;          // stride inside a sub-transform
@@ -252,9 +328,15 @@ __device__ __forceinline__ void mid_pass(double2* __restrict__ work, int nbuf,
         const int w = (GROUPS > 1) ? (int)(threadIdx.x % NBF) : (int)threadIdx.x + it * NT;
         const int b = w >> LOGSS, q = w & (SS - 1);
         const int pos0 = (b << LOGLC) + q;
-        double2 t[R];
+        // the R-1 twiddles W_Lc^{q m} of this thread's butterfly index live in its tensor-memory lane
+        static_assert(WPT == 1, "twiddles are per-thread constants");
+        constexpr int TMW = (4 * (R - 1) <= 4) ? 4 : (4 * (R - 1) <= 16) ? 16 : (4 * (R - 1) <= 32) ? 32 : 64;
+        double2 t[TMW / 4 + 1];
+        if (TM) tmem_load_c<TMW / 4>(tw_taddr, t + 1);
+        else {
 #pragma unroll
-        for (int m = 1; m < R; m++) t[m] = tw[((m - 1) << LOGSS) + q];
+            for (int m = 1; m < R; m++) t[m] = tw[((m - 1) << LOGSS) + q];
+        }
 #pragma unroll 1
         for (int buf = grp; buf < nbuf; buf += GROUPS) {
             double2* base = work + ((size_t)buf << LOGBUF);
@@ -277,23 +359,23 @@ __device__ __forceinline__ void mid_pass(double2* __restrict__ work, int nbuf,
 }
 
 template <class P, bool INV>
-__device__ __forceinline__ void mid_passes(double2* work, int nbuf, const double2* tw_s) {
+__device__ __forceinline__ void mid_passes(double2* work, int nbuf, const TwCtx& tw) {
     if (!INV) {
-        if (P::LRA) {
-            mid_pass<P::LRA, P::LOGL1, P::LOGBUF, P::NT, false>(work, nbuf, tw_s);
+        if constexpr (P::LRA > 0) {
+            mid_pass<P::LRA, P::LOGL1, P::LOGBUF, P::NT, false, P::TMEM_TW>(work, nbuf, tw.tA, tw.sA);
             __syncthreads();
         }
-        if (P::LRB) {
-            mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, P::NT, false>(work, nbuf, tw_s + P::TWA);
+        if constexpr (P::LRB > 0) {
+            mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, P::NT, false, P::TMEM_TW>(work, nbuf, tw.tB, tw.sB);
             __syncthreads();
         }
     } else {
-        if (P::LRB) {
-            mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, P::NT, true>(work, nbuf, tw_s + P::TWA);
+        if constexpr (P::LRB > 0) {
+            mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, P::NT, true, P::TMEM_TW>(work, nbuf, tw.tB, tw.sB);
             __syncthreads();
         }
-        if (P::LRA) {
-            mid_pass<P::LRA, P::LOGL1, P::LOGBUF, P::NT, true>(work, nbuf, tw_s);
+        if constexpr (P::LRA > 0) {
+            mid_pass<P::LRA, P::LOGL1, P::LOGBUF, P::NT, true, P::TMEM_TW>(work, nbuf, tw.tA, tw.sA);
             __syncthreads();
         }
     }
@@ -340,9 +422,9 @@ __device__ __forceinline__ void stage1_gather(const double2* src_buf, int j2, co
 }
 
 template <class P>
-__device__ __forceinline__ void load_T(double2* T, const double2* __restrict__ twT, int j2) {
+__device__ __forceinline__ void load_T(double2* T, const TwCtx& tw, int j2) {
 #pragma unroll
-    for (int t1 = 0; t1 < P::R1; t1++) T[t1] = __ldg(&twT[((size_t)t1 << P::LOGL1) + j2]);
+    for (int t1 = 0; t1 < P::R1; t1++) T[t1] = __ldg(&tw.twT[((size_t)t1 << P::LOGL1) + j2]);
 }
 
 // slot (index inside one polynomial's CTA slice) -> coefficient index
@@ -364,7 +446,7 @@ __device__ __forceinline__ size_t ggsw_slice(int j, int o, int k, int rank) {
 // level*base_log bits fit 30 bits (halves the registers of the decomposition state).
 template <class P, typename ST>
 __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* __restrict__ work, int rank, int a,
-                                         const PbsGeom& g, const double2* __restrict__ twT) {
+                                         const PbsGeom& g, const TwCtx& tw) {
     constexpr int C = P::C, R1 = P::R1, NT = P::NT, Q = P::Q, N = P::N;
     const int k = g.k, level = g.level, base_log = g.base_log;
     const ST mask = (ST)((1ULL << base_log) - 1);
@@ -375,7 +457,7 @@ __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* _
         const int j2 = (rank << P::LOGQ) + q;
         const u64* accc = acc + ((size_t)c << P::LOGS);
         double2 T[R1];
-        load_T<P>(T, twT, j2);                  // L2 latency hides behind the rotated (remote) loads
+        load_T<P>(T, tw, j2);
         ST st[2 * R1];
         {
             // coefficient hj*L1 + j2 of X^a * ACC is +-ACC[(hj*L1 + j2 - a) mod 2N]: the low bits (owner CTA
@@ -455,14 +537,13 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
     const int k = g.k, level = g.level, J = g.J, base_log = g.base_log;
     u64* acc = reinterpret_cast<u64*>(smem_raw);                                   // [(k+1)][S]
     double2* work = reinterpret_cast<double2*>(acc + (size_t)(k + 1) * S);         // [J][BUF]
-    double2* tw_s = work + (size_t)J * BUF;                                        // [TWN]
     const int tid = threadIdx.x;
     int rank = 0;
     if (C > 1) rank = (int)cg::this_cluster().block_rank();
     const long cluster_id = blockIdx.x / C, nclusters = gridDim.x / C;
     const size_t ggsw_stride = (size_t)J * (k + 1) * C * BUF;   // double2 per CMUX iteration
 
-    for (int t = tid; t < P::TWN; t += NT) tw_s[t] = tw_mid[t];
+    const TwCtx tw = tw_setup<P>(work + (size_t)J * BUF, twT, tw_mid);
     if (g.stagger > 0) {
         // all clusters run the same phase sequence; started together they would hit the L2 (GGSW
         // streaming) and the SM-to-SM network (stage-1 scatter) at the same instants
@@ -495,14 +576,14 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
                                  (unsigned)(sizeof(double2) << P::LOGBUF));
             // ---- P1: rotate, subtract, decompose, fold+twist, radix-R1 stage, scatter to owners
             if (level * base_log <= 30)
-                p1_items<P, unsigned>(acc, work, rank, a, g, twT);
+                p1_items<P, unsigned>(acc, work, rank, a, g, tw);
             else
-                p1_items<P, u64>(acc, work, rank, a, g, twT);
+                p1_items<P, u64>(acc, work, rank, a, g, tw);
             PBS_PROF(0)
             csync<C>();
             PBS_PROF(1)
             // ---- P2: mid passes of all J buffers
-            mid_passes<P, false>(work, J, tw_s);
+            mid_passes<P, false>(work, J, tw);
             PBS_PROF(2)
             // ---- P3: last forward pass + multiply-accumulate against GGSW_i + first inverse pass
             {
@@ -561,7 +642,7 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
             __syncthreads();
             PBS_PROF(3)
             // ---- P4: inverse mid passes of the k+1 output buffers
-            mid_passes<P, true>(work, k + 1, tw_s);
+            mid_passes<P, true>(work, k + 1, tw);
             PBS_PROF(4)
             if (C > 1) csync<C>();
             PBS_PROF(5)
@@ -571,7 +652,7 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
                 const int o = it >> P::LOGQ, q = it & (Q - 1);
                 const int j2 = (rank << P::LOGQ) + q;
                 double2 T[R1];
-                load_T<P>(T, twT, j2);
+                load_T<P>(T, tw, j2);
                 double2 z[R1];
                 stage1_gather<P>(work + ((size_t)o << P::LOGBUF), j2, T, g, z);
                 u64* acco = acc + ((size_t)o << P::LOGS);
@@ -602,6 +683,7 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
         // the same thread re-initialises the same ACC words at the top of the loop
         PBS_PROF(8)
     }
+    tw_teardown<P>(tw);
 #undef PBS_PROF
 }
 
@@ -610,12 +692,12 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
 // last radix-RF pass.
 template <class P, class Src>
 __device__ __forceinline__ void forward_poly(double2* work, int buf, int rank, const PbsGeom& g,
-                                             const double2* __restrict__ twT, Src src) {
+                                             const TwCtx& tw, Src src) {
 #pragma unroll 1
     for (int q = threadIdx.x; q < P::Q; q += P::NT) {
         const int j2 = (rank << P::LOGQ) + q;
         double2 T[P::R1];
-        load_T<P>(T, twT, j2);
+        load_T<P>(T, tw, j2);
         double re[P::R1], im[P::R1];
 #pragma unroll
         for (int j1 = 0; j1 < P::R1; j1++) {
@@ -637,18 +719,17 @@ k_bsk_fourier(double2* __restrict__ outF, const u64* __restrict__ bsk, long npol
     constexpr int C = P::C, NT = P::NT, RF = P::RF, BUF = P::BUF, N = P::N;
     constexpr int NG = BUF / RF;
     double2* work = reinterpret_cast<double2*>(smem_raw);   // [BUF]
-    double2* tw_s = work + BUF;
     const int k = g.k, level = g.level;
     int rank = 0;
     if (C > 1) rank = (int)cg::this_cluster().block_rank();
     const long cluster_id = blockIdx.x / C, nclusters = gridDim.x / C;
-    for (int t = threadIdx.x; t < P::TWN; t += NT) tw_s[t] = tw_mid[t];
+    const TwCtx tw = tw_setup<P>(work + BUF, twT, tw_mid);
     csync<C>();
     for (long p = cluster_id; p < npoly; p += nclusters) {
         const u64* src = bsk + (size_t)p * N;
-        forward_poly<P>(work, 0, rank, g, twT, [&](int coef) { return (double)(i64)src[coef]; });
+        forward_poly<P>(work, 0, rank, g, tw, [&](int coef) { return (double)(i64)src[coef]; });
         csync<C>();
-        mid_passes<P, false>(work, 1, tw_s);
+        mid_passes<P, false>(work, 1, tw);
         // p = ((i*level + lv)*(k+1) + r)*(k+1) + o
         const int o = (int)(p % (k + 1));
         const int r = (int)((p / (k + 1)) % (k + 1));
@@ -666,6 +747,7 @@ k_bsk_fourier(double2* __restrict__ outF, const u64* __restrict__ bsk, long npol
         }
         csync<C>();
     }
+    tw_teardown<P>(tw);
 }
 
 // ---- debug / test entry: out = a_small * b_torus in Z_2^64[X]/(X^N+1) through the same fp64
@@ -680,19 +762,18 @@ k_polymul_test(u64* __restrict__ out, const i64* __restrict__ a_small, const u64
     constexpr int C = P::C, R1 = P::R1, NT = P::NT, RF = P::RF, BUF = P::BUF, N = P::N, M = P::M, Q = P::Q;
     constexpr int NG = BUF / RF;
     double2* work = reinterpret_cast<double2*>(smem_raw);   // [2][BUF]
-    double2* tw_s = work + 2 * BUF;
     int rank = 0;
     if (C > 1) rank = (int)cg::this_cluster().block_rank();
     const long cluster_id = blockIdx.x / C, nclusters = gridDim.x / C;
-    for (int t = threadIdx.x; t < P::TWN; t += NT) tw_s[t] = tw_mid[t];
+    const TwCtx tw = tw_setup<P>(work + 2 * BUF, twT, tw_mid);
     csync<C>();
     for (long p = cluster_id; p < npoly; p += nclusters) {
         const i64* pa = a_small + (size_t)p * N;
         const u64* pb = b_torus + (size_t)p * N;
-        forward_poly<P>(work, 0, rank, g, twT, [&](int coef) { return (double)pa[coef]; });
-        forward_poly<P>(work, 1, rank, g, twT, [&](int coef) { return (double)(i64)pb[coef]; });
+        forward_poly<P>(work, 0, rank, g, tw, [&](int coef) { return (double)pa[coef]; });
+        forward_poly<P>(work, 1, rank, g, tw, [&](int coef) { return (double)(i64)pb[coef]; });
         csync<C>();
-        mid_passes<P, false>(work, 2, tw_s);
+        mid_passes<P, false>(work, 2, tw);
         for (int w = threadIdx.x; w < NG; w += NT) {
             double2 x[RF], y[RF];
 #pragma unroll
@@ -709,12 +790,12 @@ k_polymul_test(u64* __restrict__ out, const i64* __restrict__ a_small, const u64
             for (int m = 0; m < RF; m++) work[SW(w * RF + m)] = x[m];
         }
         __syncthreads();
-        mid_passes<P, true>(work, 1, tw_s);
+        mid_passes<P, true>(work, 1, tw);
         csync<C>();
         for (int q = threadIdx.x; q < Q; q += NT) {
             const int j2 = (rank << P::LOGQ) + q;
             double2 T[R1];
-            load_T<P>(T, twT, j2);
+            load_T<P>(T, tw, j2);
             double2 z[R1];
             stage1_gather<P>(work, j2, T, g, z);
 #pragma unroll
@@ -725,11 +806,13 @@ k_polymul_test(u64* __restrict__ out, const i64* __restrict__ a_small, const u64
         }
         csync<C>();
     }
+    tw_teardown<P>(tw);
 }
 
 // ------------------------------------------------------------------ host launch helpers ----
 template <typename Kern, typename... Args>
-static int launch_clustered(Kern kern, int C, int NT, size_t smem, long work_items, cudaStream_t st, Args... args) {
+static int launch_clustered(Kern kern, int C, int NT, int tmem_cols, size_t smem, long work_items, cudaStream_t st,
+                            Args... args) {
     FHE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
     FHE_CUDA(cudaGetDevice(&dev));
@@ -755,6 +838,7 @@ static int launch_clustered(Kern kern, int C, int NT, size_t smem, long work_ite
         int per_sm = 0;
         FHE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
         if (per_sm < 1) FHE_FAIL(4, "pbs: kernel does not fit on an SM (smem %zu)", smem);
+        if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;      // tensor-memory columns per SM
         nclusters = per_sm * sms;
     }
     if ((long)nclusters > work_items) nclusters = (int)work_items;
@@ -781,23 +865,23 @@ template <class P>
 struct PbsPlanOps {
     static PbsPlanMeta meta() {
         return PbsPlanMeta{P::C, P::LOGR1, P::LRA, P::LRB, P::LRF, P::NT, P::MINB, P::KMAX, P::LOGM,
-                           (long)sizeof(double2) * P::TWN};
+                           (long)sizeof(double2) * P::TW_SMEM};
     }
     static size_t smem_pbs(const PbsGeom& g) {
-        return (size_t)(g.k + 1) * P::S * 8 + (size_t)g.J * P::BUF * 16 + (size_t)P::TWN * 16;
+        return (size_t)(g.k + 1) * P::S * 8 + (size_t)g.J * P::BUF * 16 + (size_t)P::TW_SMEM * 16;
     }
     static int pbs(const PbsLaunchArgs& a) {
-        return launch_clustered(k_pbs<P>, P::C, P::NT, smem_pbs(a.g), a.B, a.st, a.out, a.in, a.B, a.bskF, a.luts,
+        return launch_clustered(k_pbs<P>, P::C, P::NT, P::TM_CTA, smem_pbs(a.g), a.B, a.st, a.out, a.in, a.B, a.bskF, a.luts,
                                 a.lut_idx, a.g, a.twT, a.tw_mid, a.prof);
     }
     static int bsk(const PbsLaunchArgs& a) {
-        const size_t smem = (size_t)P::BUF * 16 + (size_t)P::TWN * 16;
-        return launch_clustered(k_bsk_fourier<P>, P::C, P::NT, smem, a.npoly, a.st, a.outF, a.bsk, a.npoly, a.g,
+        const size_t smem = (size_t)P::BUF * 16 + (size_t)P::TW_SMEM * 16;
+        return launch_clustered(k_bsk_fourier<P>, P::C, P::NT, P::TM_CTA, smem, a.npoly, a.st, a.outF, a.bsk, a.npoly, a.g,
                                 a.twT, a.tw_mid);
     }
     static int polymul(const PbsLaunchArgs& a) {
-        const size_t smem = (size_t)2 * P::BUF * 16 + (size_t)P::TWN * 16;
-        return launch_clustered(k_polymul_test<P>, P::C, P::NT, smem, a.npoly, a.st, a.pm_out, a.pm_a, a.pm_b,
+        const size_t smem = (size_t)2 * P::BUF * 16 + (size_t)P::TW_SMEM * 16;
+        return launch_clustered(k_polymul_test<P>, P::C, P::NT, P::TM_CTA, smem, a.npoly, a.st, a.pm_out, a.pm_a, a.pm_b,
                                 a.npoly, a.g, a.twT, a.tw_mid);
     }
 };

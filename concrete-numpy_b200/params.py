@@ -36,12 +36,12 @@ def secure_log2_std(dim: int) -> float:
     return max(SECURITY_SLOPE * dim + SECURITY_BIAS, MIN_LOG2_STD)
 
 
-# (C, logM, lra, lrb, lrf, kmax) of every FFT plan instantiated in csrc/pbs_inst_{a,b,c}.cu
+# (C, logM, lra, lrb, lrf, kmax, minb) of every FFT plan instantiated in csrc/pbs_inst_{a,b,c}.cu
 _PBS_PLANS = [
-    (1, 9, 3, 0, 3, 1), (1, 8, 3, 0, 3, 1), (1, 7, 3, 0, 3, 1),
-    (1, 7, 3, 0, 2, 3), (1, 8, 3, 0, 2, 3), (1, 9, 3, 0, 2, 3), (1, 10, 4, 0, 2, 3),
-    (2, 12, 4, 4, 3, 1), (2, 11, 4, 3, 3, 1), (1, 11, 4, 0, 3, 1), (1, 10, 4, 0, 3, 1),
-    (8, 14, 4, 4, 3, 1), (8, 13, 4, 3, 3, 1), (4, 13, 4, 4, 3, 1), (4, 12, 4, 3, 3, 1),
+    (1, 9, 3, 0, 3, 1, 3), (1, 8, 3, 0, 3, 1, 3), (1, 7, 3, 0, 3, 1, 1),
+    (1, 7, 3, 0, 2, 3, 1), (1, 8, 3, 0, 2, 3, 1), (1, 9, 3, 0, 2, 3, 1), (1, 10, 4, 0, 2, 3, 1),
+    (2, 12, 4, 4, 3, 1, 1), (2, 11, 4, 3, 3, 1, 2), (1, 11, 4, 0, 3, 1, 1), (1, 10, 4, 0, 3, 1, 3),
+    (16, 14, 4, 3, 3, 1, 2), (8, 14, 4, 4, 3, 1, 1), (8, 13, 4, 3, 3, 1, 2), (4, 13, 4, 4, 3, 1, 1), (4, 12, 4, 3, 3, 1, 2),
 ]
 
 
@@ -50,16 +50,17 @@ def pbs_cluster_size(N: int, k: int, level: int) -> int:
     logM = N.bit_length() - 2
     if N != (2 << logM) or not 8 <= logM + 1 <= 15 or not 1 <= k <= 3 or not 1 <= level <= 4:
         return -1
-    for C in (1, 2, 4, 8):
-        for (pc, plogM, lra, lrb, lrf, kmax) in _PBS_PLANS:
+    for C in (1, 2, 4, 8, 16):
+        for (pc, plogM, lra, lrb, lrf, kmax, minb) in _PBS_PLANS:
             if pc != C or plogM != logM or k > kmax or (k <= 1 and kmax > 1):
                 continue
             logL1 = lra + lrb + lrf
-            tw = 0
-            if lra:
-                tw += ((1 << lra) - 1) << (logL1 - lra)
-            if lrb:
-                tw += ((1 << lrb) - 1) << lrf
+            tw = 0          # twiddles live in tensor memory for the one-CTA-per-SM plans (minb == 1)
+            if minb != 1:
+                if lra:
+                    tw += ((1 << lra) - 1) << (logL1 - lra)
+                if lrb:
+                    tw += ((1 << lrb) - 1) << lrf
             buf = (1 << logM) // C if C > 1 else (1 << logM)
             smem = (k + 1) * (N // C) * 8 + (k + 1) * level * buf * 16 + tw * 16
             if smem <= SMEM_MAX:
