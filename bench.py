@@ -188,17 +188,16 @@ def run_ours(args):
 
     # instrument the bootstrap launches with CUDA events (torch's current stream = launch stream)
     pbs_events = []
-    raw_bootstrap = E.bootstrap
+    raw_pbs_launch = E.pbs_launch
 
-    def timed_bootstrap(*a, **k):
+    def timed_pbs_launch(ev_, out_, small_, count, luts_, idx_):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = raw_bootstrap(*a, **k)
+        raw_pbs_launch(ev_, out_, small_, count, luts_, idx_)
         e1.record()
-        pbs_events.append((e0, e1, a[1].shape[0]))
-        return out
+        pbs_events.append((e0, e1, count))
 
-    E.bootstrap = timed_bootstrap
+    E.pbs_launch = timed_pbs_launch
 
     def step_resident():
         return circuit.server.run(enc, ev)

@@ -213,19 +213,80 @@ def keyswitch(ev: EvalKeys, ct: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pbs_launch(ev: EvalKeys, out: torch.Tensor, ct_small: torch.Tensor, count: int, luts: torch.Tensor,
+               lut_idx: Optional[torch.Tensor]) -> None:
+    """One fhe_pbs_batch launch on the current stream: `count` ciphertexts from `ct_small` into `out`."""
+    p = ev.params
+    _lib.call("fhe_pbs_batch", out.data_ptr(), ct_small.data_ptr(), count, ev.bsk_f.data_ptr(),
+              luts.data_ptr(), _ptr(lut_idx), p.n, p.k, p.N, p.pbs_level, p.pbs_base_log, _stream())
+
+
 def bootstrap(ev: EvalKeys, ct_small: torch.Tensor, luts: torch.Tensor, lut_idx: Optional[torch.Tensor]) -> torch.Tensor:
     p = ev.params
     E = ct_small.numel() // (p.n + 1)
     out = torch.empty((E, p.ct_words), dtype=torch.int64, device=ct_small.device)
     with torch.cuda.device(ct_small.device):
-        _lib.call("fhe_pbs_batch", out.data_ptr(), ct_small.data_ptr(), E, ev.bsk_f.data_ptr(),
-                  luts.data_ptr(), _ptr(lut_idx), p.n, p.k, p.N, p.pbs_level, p.pbs_base_log, _stream())
+        pbs_launch(ev, out, ct_small, E, luts, lut_idx)
     return out
 
 
+_SIDE_STREAMS = {}
+PIPELINE_MIN_CHUNK = 480          # ciphertexts; below 2 chunks of this size the lookup is not pipelined
+PIPELINE_MAX_CHUNKS = 4
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def table_lookup(ev: EvalKeys, ct: torch.Tensor, luts: torch.Tensor, lut_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """FHE.apply_lookup_table = keyswitch + programmable bootstrap per element."""
-    return bootstrap(ev, keyswitch(ev, ct), luts, lut_idx)
+    """FHE.apply_lookup_table = keyswitch + programmable bootstrap per element.
+
+    Large batches are cut into chunks and software-pipelined over two streams: the bootstrap of chunk i
+    (thread-block clusters, which cannot cover every SM of the chip: 15 clusters of 8 on a B200) runs
+    on the current stream while the keyswitch of chunk i+1 runs on a side stream on the SMs the clusters
+    leave idle.  Results are identical to the unchunked call (ciphertexts are independent)."""
+    p = ev.params
+    ct = ct.contiguous()
+    E = ct.numel() // p.ct_words
+    n_chunks = min(PIPELINE_MAX_CHUNKS, E // PIPELINE_MIN_CHUNK)
+    if n_chunks < 2:
+        return bootstrap(ev, keyswitch(ev, ct), luts, lut_idx)
+    ct = ct.view(E, p.ct_words)
+    dev = ct.device
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    bounds = [(E * i) // n_chunks for i in range(n_chunks + 1)]
+    small = torch.empty((E, p.n + 1), dtype=torch.int64, device=dev)
+    out = torch.empty((E, p.ct_words), dtype=torch.int64, device=dev)
+
+    def ks(i):
+        lo, hi = bounds[i], bounds[i + 1]
+        _lib.call("fhe_keyswitch_batch", small[lo:hi].data_ptr(), ct[lo:hi].data_ptr(), hi - lo, ev.ksk.data_ptr(),
+                  p.big_dim, p.n, p.ks_level, p.ks_base_log, _stream())
+
+    def pbs(i):
+        lo, hi = bounds[i], bounds[i + 1]
+        idx = None if lut_idx is None else lut_idx[lo:hi]
+        pbs_launch(ev, out[lo:hi], small[lo:hi], hi - lo, luts, idx)
+
+    with torch.cuda.device(dev):
+        ready = torch.cuda.Event()
+        ready.record(main)                   # inputs (and the buffers above) are ready on the main stream
+        side.wait_event(ready)
+        ks(0)
+        for i in range(n_chunks):
+            pbs(i)                           # enqueued first: the clusters take their SMs ...
+            if i + 1 < n_chunks:
+                with torch.cuda.stream(side):
+                    ks(i + 1)                # ... and the next keyswitch fills the SMs they cannot use
+                    done = torch.cuda.Event()
+                    done.record(side)
+                main.wait_event(done)
+    return out
 
 
 def _rows(t: torch.Tensor, L: int) -> int:
