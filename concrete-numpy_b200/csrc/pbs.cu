@@ -177,6 +177,7 @@ int fhe_pbs_batch(u64* out, const u64* in, long B, const double2* bsk_f, const u
     if (rc) return rc;
     a.st = (cudaStream_t)stream;
     a.out = out; a.in = in; a.B = B; a.bskF = bsk_f; a.luts = luts; a.lut_idx = lut_idx; a.prof = g_prof_buf;
+    a.g.prof = g_prof_buf;
     return e->pbs(a);
 }
 

@@ -38,6 +38,7 @@ struct PbsGeom {
     int J;                // (k+1)*level forward transforms per CMUX
     double inv_M;
     int dbg;              // development ablation bits (FHE_PBS_DBG), 0 in production
+    long long* prof;      // phase-cycle buffer (fhe_pbs_set_profile) or null
     int stagger;          // start-up delay per cluster id (SM cycles), de-synchronises the clusters' phases
     double2 cj[16];       // exp(i*pi*j1/(2*R1)), j1 < R1
 };
@@ -451,8 +452,10 @@ __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* _
     const int k = g.k, level = g.level, base_log = g.base_log;
     const ST mask = (ST)((1ULL << base_log) - 1);
     const int nonrep = 64 - level * base_log;
+    const bool do_prof = (g.prof != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
 #pragma unroll 1
     for (int it = threadIdx.x; it < ((k + 1) << P::LOGQ); it += NT) {
+        const long long t_a = do_prof ? clock64() : 0;
         const int c = it >> P::LOGQ, q = it & (Q - 1);
         const int j2 = (rank << P::LOGQ) + q;
         const u64* accc = acc + ((size_t)c << P::LOGS);
@@ -493,6 +496,12 @@ __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* _
                 }
             }
         }
+        if (do_prof) {
+            // touch the last state word so that the timestamp waits for the loads
+            const long long t_b = clock64() + (long long)(st[2 * R1 - 1] & 0);
+            g.prof[9] += t_b - t_a;
+        }
+        const long long t_c = do_prof ? clock64() : 0;
 #pragma unroll 1
         for (int t = 0; t < level; t++) {
             const int lv = level - 1 - t;       // digits come out least significant level first
@@ -511,6 +520,7 @@ __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* _
             }
             stage1_emit<P>(work + ((size_t)(c * level + lv) << P::LOGBUF), j2, re, im, T, g);
         }
+        if (do_prof) g.prof[10] += clock64() - t_c;
     }
 }
 

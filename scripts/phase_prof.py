@@ -35,5 +35,7 @@ for pbits, B in ((8, 36), (6, 148), (4, 888)):
           f"=> {c.sum() / (ms * 1e-3) / 1e6:.0f} MHz")
     for nm, v in zip(NAMES, c):
         print(f"   {nm:18s} {v / max(c.sum(), 1) * 100:5.1f}%   {v / 1e3:10.0f} kcycles")
+    extra = prof.cpu().numpy()[9:11].astype(np.float64)
+    print(f"   (thread 0 inside P1: loads+diff {extra[0] / 1e3:.0f} kcycles, level loop {extra[1] / 1e3:.0f} kcycles)")
     del ks, ev
     torch.cuda.empty_cache()
