@@ -167,17 +167,40 @@ class LibraryCompilationResult(CompilationResult):
     pass
 
 
+_SHARD_GROUP = None
+
+
+def set_shard_group(group) -> None:
+    """Shard every table lookup of subsequent `server_call`s by ciphertext over the ranks of `group`
+    (a torch.distributed process group, e.g. `dist.group.WORLD`; None switches sharding off).  All ranks
+    must then call `Server.run` with the same arguments; keys are replicated (deterministic keygen)."""
+    global _SHARD_GROUP
+    _SHARD_GROUP = group
+
+
+def _shard_group():
+    if _SHARD_GROUP is not None:
+        return _SHARD_GROUP
+    if os.environ.get("CNP_B200_SHARD", "0") not in ("", "0"):
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return dist.group.WORLD
+    return None
+
+
 class ServerLambda:
-    """Executable form of a compiled program: one Executor per device, created lazily."""
+    """Executable form of a compiled program: one Executor per (device, shard group), created lazily."""
 
     def __init__(self, result: CompilationResult):
         self.result = result
         self._executors: Dict[str, Executor] = {}
 
     def executor(self, device) -> Executor:
-        key = str(device)
+        group = _shard_group()
+        key = f"{device}/{id(group) if group is not None else 0}"
         if key not in self._executors:
-            self._executors[key] = Executor(self.result.program, self.result.crypto, device)
+            self._executors[key] = Executor(self.result.program, self.result.crypto, device, group=group)
         return self._executors[key]
 
 
