@@ -122,6 +122,8 @@ PBS_CASES = [
     (7, 12, 1, 16384, 2, 15),
     (8, 12, 1, 32768, 2, 15),
     (4, 16, 1, 8192, 3, 10),
+    (4, 8, 1, 32768, 3, 10),      # 16-CTA cluster plan (two clusters per SM)
+    (3, 12, 1, 4096, 3, 10),      # 2-CTA cluster plan with 1024-point local transforms
 ]
 
 
