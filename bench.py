@@ -283,6 +283,9 @@ def run_ours(args):
                        "decrypted_output_correct": correct},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "traffic_note": "ncu --set full on a one-wave launch (15 ciphertexts): dram read 2.09 GB = the Fourier "
+                                         "BSK streamed once per wave (profiles/r01_pbs_p8_v3_ncu_summary.txt); a bench launch of "
+                                         "4096 ciphertexts is 274 such waves; fp64-bound kernel, HBM share of peak < 2 %",
                          "kernel": "k_pbs", "launches_timed": n_pbs_launch, "mean_launch_ms": pbs_ms / max(n_pbs_launch, 1),
                          "flops_per_pbs": fl, "share_of_step": pbs_ms / ms if ms else None,
                          "peak_source": "DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no fp64 entry)"},
