@@ -218,6 +218,32 @@ __device__ __forceinline__ double2 ld_cluster_f64x2(unsigned addr) {
 __device__ __forceinline__ void st_cluster_f64x2(unsigned addr, double2 v) {
     asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
 }
+// mbarrier plumbing and bulk asynchronous copies between the shared memories of a cluster: the inverse
+// exchange of the FFT is PUSHED by the copy engine in 4 KiB chunks (measured ~2-3x the throughput of
+// element-wise remote accesses, profiles/r01_ubench_dsmem_bulk.log) and the receiver waits for its own data
+__device__ __forceinline__ void mbar_init(u64* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arm(u64* bar, unsigned tx_bytes) {      // one arrival + expected bytes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(tx_bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_to_cluster(unsigned dst_cluster_addr, const void* src, unsigned bytes,
+                                                     unsigned mbar_cluster_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster_addr), "r"(smem_u32(src)), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// relaxed: the arrival only says "my READS of the spare buffers are done" (their values were consumed before
+// the preceding __syncthreads), so no memory fence (MEMBAR.ALL.GPU) is needed
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // L2 prefetch of a contiguous global range (bytes multiple of 16)
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -422,6 +448,21 @@ __device__ __forceinline__ void stage1_gather(const double2* src_buf, int j2, co
     for (int j1 = 0; j1 < P::R1; j1++) z[j1] = (j1 == 0) ? v[0] : cmulc(v[j1], g.cj[j1]);
 }
 
+// inverse of stage 1 when the sub-transform outputs were pushed into this CTA: chunk t1 of `recv` holds the
+// Q values CTA t1 computed for this CTA's j2 range (still in the senders' swizzle)
+template <class P>
+__device__ __forceinline__ void stage1_gather_local(const double2* recv, int q, const double2* T, const PbsGeom& g,
+                                                    double2* z) {
+    double2 v[P::R1];
+#pragma unroll
+    for (int t1 = 0; t1 < P::R1; t1++) v[t1] = recv[(t1 << P::LOGQ) + SW(q)];
+#pragma unroll
+    for (int t1 = 0; t1 < P::R1; t1++) v[t1] = cmulc(v[t1], T[t1]);
+    Dft<P::R1, true>::run(v);
+#pragma unroll
+    for (int j1 = 0; j1 < P::R1; j1++) z[j1] = (j1 == 0) ? v[0] : cmulc(v[j1], g.cj[j1]);
+}
+
 template <class P>
 __device__ __forceinline__ void load_T(double2* T, const TwCtx& tw, int j2) {
 #pragma unroll
@@ -554,6 +595,18 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
     const size_t ggsw_stride = (size_t)J * (k + 1) * C * BUF;   // double2 per CMUX iteration
 
     const TwCtx tw = tw_setup<P>(work + (size_t)J * BUF, twT, tw_mid);
+    // cluster plans with at least k+1 spare work buffers (level >= 2): the inverse exchange is pushed with
+    // bulk copies into the peers' spare buffers and counted on one mbarrier per output polynomial
+    __shared__ __align__(8) u64 s_bar_inv[4];
+    const bool push_inv = (C >= 4) && (J >= 2 * (k + 1)) && !(g.dbg & 32);   // C == 2: the TPC-pair path is fast enough
+    unsigned inv_phase = 0;
+    if (C > 1) {
+        if (tid == 0) {
+            for (int o = 0; o <= k; o++) mbar_init(&s_bar_inv[o], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
     if (g.stagger > 0) {
         // all clusters run the same phase sequence; started together they would hit the L2 (GGSW
         // streaming) and the SM-to-SM network (stage-1 scatter) at the same instants
@@ -584,6 +637,8 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
             if (i + 1 < g.n && tid < J * (k + 1) && !(g.dbg & 16))
                 prefetch_l2_bulk(bskF + (size_t)(i + 1) * ggsw_stride + (((size_t)tid * C + rank) << P::LOGBUF),
                                  (unsigned)(sizeof(double2) << P::LOGBUF));
+            if (push_inv && tid == 0)
+                for (int o = 0; o <= k; o++) mbar_arm(&s_bar_inv[o], (unsigned)(sizeof(double2) << P::LOGBUF));
             // ---- P1: rotate, subtract, decompose, fold+twist, radix-R1 stage, scatter to owners
             if (level * base_log <= 30)
                 p1_items<P, unsigned>(acc, work, rank, a, g, tw);
@@ -650,21 +705,42 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
                 }
             }
             __syncthreads();
+            if (push_inv) cluster_arrive();      // "my spare buffers are free": completes behind the inverse passes
             PBS_PROF(3)
             // ---- P4: inverse mid passes of the k+1 output buffers
             mid_passes<P, true>(work, k + 1, tw);
             PBS_PROF(4)
-            if (C > 1) csync<C>();
+            if (push_inv) {
+                cluster_wait();
+                if (tid < (k + 1) * C) {
+                    // chunk [d*Q, (d+1)*Q) of my output buffer o -> chunk `rank` of CTA d's spare buffer k+1+o
+                    const int o = tid / C, d = tid % C;
+                    fence_proxy_async();
+                    const double2* src = work + ((size_t)o << P::LOGBUF) + (d << P::LOGQ);
+                    const double2* dst = work + ((size_t)(k + 1 + o) << P::LOGBUF) + (rank << P::LOGQ);
+                    bulk_copy_to_cluster(mapa_u32(smem_u32(dst), d), src, (unsigned)(sizeof(double2) << P::LOGQ),
+                                         mapa_u32(smem_u32(&s_bar_inv[o]), d));
+                }
+            } else if (C > 1)
+                csync<C>();
             PBS_PROF(5)
             // ---- P5: gather from owners, inverse radix-R1 stage, untwist, round, ACC +=
 #pragma unroll 1
+            int o_ready = -1;
             for (int it = tid; it < ((k + 1) << P::LOGQ); it += NT) {
                 const int o = it >> P::LOGQ, q = it & (Q - 1);
                 const int j2 = (rank << P::LOGQ) + q;
                 double2 T[R1];
                 load_T<P>(T, tw, j2);
                 double2 z[R1];
-                stage1_gather<P>(work + ((size_t)o << P::LOGBUF), j2, T, g, z);
+                if (push_inv) {
+                    if (o != o_ready) {              // wait for the C chunks of output o (the others still fly)
+                        mbar_wait(&s_bar_inv[o], inv_phase & 1);
+                        o_ready = o;
+                    }
+                    stage1_gather_local<P>(work + ((size_t)(k + 1 + o) << P::LOGBUF), q, T, g, z);
+                } else
+                    stage1_gather<P>(work + ((size_t)o << P::LOGBUF), j2, T, g, z);
                 u64* acco = acc + ((size_t)o << P::LOGS);
 #pragma unroll
                 for (int j1 = 0; j1 < R1; j1++) {
@@ -672,6 +748,7 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
                     acco[((R1 + j1) << P::LOGQ) + q] += f2torus(z[j1].y * g.inv_M);
                 }
             }
+            inv_phase++;
             PBS_PROF(6)
             csync<C>();
             PBS_PROF(7)
