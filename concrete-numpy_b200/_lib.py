@@ -29,6 +29,12 @@ _SIGS = {
     "fhe_bsk_fourier_elems": (C.c_long, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "fhe_bsk_to_fourier": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_pbs_batch": (C.c_int, [_p, _p, C.c_long, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
+    "fhe_pbs_num_variants": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "fhe_pbs_variant_cluster_size": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fhe_pbs_variant_capacity": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fhe_bsk_to_fourier_variant": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
+    "fhe_bsk_relayout": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
+    "fhe_pbs_batch_variant": (C.c_int, [_p, _p, C.c_long, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_pbs_set_profile": (C.c_int, [_p]),
     "fhe_debug_polymul": (C.c_int, [_p, _p, _p, C.c_long, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_lin_add": (C.c_int, [_p, _p, _p, _p, _p, C.c_long, C.c_int, _p]),

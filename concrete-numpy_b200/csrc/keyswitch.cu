@@ -16,7 +16,10 @@
 #define KS_IC 32      // mask words decomposed per shared-memory chunk
 #define KS_MAXL 16
 
-template <int BT>
+// SPLITK: small batches (steps of sequential circuits) do not fill the GPU with (batch tile x column tile)
+// CTAs, so blockIdx.z additionally splits the kN mask words; partial sums are combined with 64-bit atomic
+// adds into a zero-initialised output -- wrapping sums are order independent, the result stays bit-exact.
+template <int BT, bool SPLITK>
 __global__ void __launch_bounds__(KS_COLS)
 k_keyswitch(u64* __restrict__ out, const u64* __restrict__ in, long B, const u64* __restrict__ ksk,
             int kN, int n, int level, int base_log) {
@@ -25,15 +28,21 @@ k_keyswitch(u64* __restrict__ out, const u64* __restrict__ in, long B, const u64
     const long b0 = (long)blockIdx.x * BT;
     const bool col_ok = j <= n;
     const int L_in = kN + 1, L_out = n + 1;
+    int i_begin = 0, i_end = kN;
+    if (SPLITK) {
+        const int per = ((kN + gridDim.z - 1) / gridDim.z + KS_IC - 1) / KS_IC * KS_IC;
+        i_begin = blockIdx.z * per;
+        i_end = min(kN, i_begin + per);
+    }
 
     u64 acc[BT];
 #pragma unroll
     for (int b = 0; b < BT; b++) {
         long e = b0 + b;
-        acc[b] = (j == n && e < B) ? in[(size_t)e * L_in + kN] : 0ULL;
+        acc[b] = (j == n && e < B && (!SPLITK || blockIdx.z == 0)) ? in[(size_t)e * L_in + kN] : 0ULL;
     }
 
-    for (int i0 = 0; i0 < kN; i0 += KS_IC) {
+    for (int i0 = i_begin; i0 < i_end; i0 += KS_IC) {
         __syncthreads();
         // decompose BT x KS_IC mask words into shared memory
         for (int t = threadIdx.x; t < BT * KS_IC; t += KS_COLS) {
@@ -43,14 +52,14 @@ k_keyswitch(u64* __restrict__ out, const u64* __restrict__ in, long B, const u64
             int dg[KS_MAXL];
 #pragma unroll
             for (int q = 0; q < KS_MAXL; q++) dg[q] = 0;
-            if (e < B && i < kN) signed_decompose<KS_MAXL>(in[(size_t)e * L_in + i], base_log, level, dg);
+            if (e < B && i < i_end) signed_decompose<KS_MAXL>(in[(size_t)e * L_in + i], base_log, level, dg);
 #pragma unroll
             for (int q = 0; q < KS_MAXL; q++)
                 if (q < level) s_dig[(ii * level + (level - 1 - q)) * BT + b] = dg[q];  // dg[q] <-> level (level-q)
         }
         __syncthreads();
         if (col_ok) {
-            const int imax = min(KS_IC, kN - i0);
+            const int imax = min(KS_IC, i_end - i0);
             const u64* krow = ksk + (size_t)i0 * level * L_out + j;
             for (int r = 0; r < imax * level; r++) {
                 const u64 kv = __ldg(krow + (size_t)r * L_out);
@@ -70,7 +79,11 @@ k_keyswitch(u64* __restrict__ out, const u64* __restrict__ in, long B, const u64
 #pragma unroll
         for (int b = 0; b < BT; b++) {
             long e = b0 + b;
-            if (e < B) out[(size_t)e * L_out + j] = acc[b];
+            if (e < B) {
+                if (SPLITK) atomicAdd(reinterpret_cast<unsigned long long*>(out + (size_t)e * L_out + j),
+                                      (unsigned long long)acc[b]);
+                else out[(size_t)e * L_out + j] = acc[b];
+            }
         }
     }
 }
@@ -86,18 +99,27 @@ extern "C" int fhe_keyswitch_batch(u64* out, const u64* in, long B, const u64* k
     if (B >= 512) {
         const int BT = 32;
         size_t smem = (size_t)KS_IC * level * BT * sizeof(int);
-        k_keyswitch<BT><<<dim3((unsigned)((B + BT - 1) / BT), ycols), KS_COLS, smem, st>>>(
-            out, in, B, ksk, kN, n, level, base_log);
-    } else if (B >= 32) {
-        const int BT = 8;
-        size_t smem = (size_t)KS_IC * level * BT * sizeof(int);
-        k_keyswitch<BT><<<dim3((unsigned)((B + BT - 1) / BT), ycols), KS_COLS, smem, st>>>(
+        k_keyswitch<BT, false><<<dim3((unsigned)((B + BT - 1) / BT), ycols), KS_COLS, smem, st>>>(
             out, in, B, ksk, kN, n, level, base_log);
     } else {
-        const int BT = 4;
+        // small batch: split the mask words too until a few CTAs per SM are in flight
+        const int BT = 8;
         size_t smem = (size_t)KS_IC * level * BT * sizeof(int);
-        k_keyswitch<BT><<<dim3((unsigned)((B + BT - 1) / BT), ycols), KS_COLS, smem, st>>>(
-            out, in, B, ksk, kN, n, level, base_log);
+        const long tiles = ((B + BT - 1) / BT) * ycols;
+        int dev = 0, sms = 0;
+        FHE_CUDA(cudaGetDevice(&dev));
+        FHE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        long ksplit = (4L * sms + tiles - 1) / tiles;
+        const long max_split = (kN + KS_IC - 1) / KS_IC;
+        if (ksplit > max_split) ksplit = max_split;
+        if (ksplit <= 1) {
+            k_keyswitch<BT, false><<<dim3((unsigned)((B + BT - 1) / BT), ycols), KS_COLS, smem, st>>>(
+                out, in, B, ksk, kN, n, level, base_log);
+        } else {
+            FHE_CUDA(cudaMemsetAsync(out, 0, sizeof(u64) * (size_t)B * (n + 1), st));
+            k_keyswitch<BT, true><<<dim3((unsigned)((B + BT - 1) / BT), ycols, (unsigned)ksplit), KS_COLS, smem, st>>>(
+                out, in, B, ksk, kN, n, level, base_log);
+        }
     }
     FHE_CHECK_LAUNCH();
     return 0;

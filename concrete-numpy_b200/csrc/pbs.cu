@@ -13,6 +13,7 @@
 const PbsPlanEntry* pbs_plans_a(int* count);
 const PbsPlanEntry* pbs_plans_b(int* count);
 const PbsPlanEntry* pbs_plans_c(int* count);
+const PbsPlanEntry* pbs_plans_d(int* count);
 
 static std::vector<PbsPlanEntry> all_plans() {
     std::vector<PbsPlanEntry> v;
@@ -23,6 +24,8 @@ static std::vector<PbsPlanEntry> all_plans() {
     v.insert(v.end(), p, p + n);
     p = pbs_plans_a(&n);
     v.insert(v.end(), p, p + n);
+    p = pbs_plans_d(&n);
+    v.insert(v.end(), p, p + n);
     return v;
 }
 
@@ -32,27 +35,26 @@ static size_t plan_smem(const PbsPlanMeta& m, int k, int level) {
     return (size_t)(k + 1) * (N / m.C) * 8 + (size_t)(k + 1) * level * buf * 16 + (size_t)m.smem_fixed;
 }
 
-// smallest cluster whose on-chip layout fits; index into all_plans() or -1
-static int choose_plan(int N, int k, int level) {
+// every plan whose on-chip layout fits (N, k, level), smallest cluster first: entry 0 is the throughput
+// plan (most ciphertexts in flight per GPU), the later ones spread one ciphertext over more SMs and
+// are used for small batches (latency plans).  Values are indices into all_plans().
+static std::vector<int> fitting_plans(int N, int k, int level) {
     static const std::vector<PbsPlanEntry> plans = all_plans();
-    const int logM = ilog2_exact(N) - 1;
-    // experiment knob: FHE_PBS_SMALL_L=1 prefers the plans with 1024-point local transforms (twice the
-    // cluster size, two clusters resident per SM so that one's exchange phases overlap the other's math)
-    const char* e = getenv("FHE_PBS_SMALL_L");
-    const bool small_l = e && atoi(e) != 0;
-    int best = -1;
+    std::vector<int> out;
+    const int logN = ilog2_exact(N);
+    if (logN < 8 || logN > 15 || k < 1 || k > 3 || level < 1 || level > 4) return out;
+    const int logM = logN - 1;
     for (int C = 1; C <= 16; C *= 2)
         for (size_t i = 0; i < plans.size(); i++) {
             const PbsPlanMeta& m = plans[i].meta;
             if (m.C != C || m.logM != logM) continue;
             if (k > m.kmax || (k <= 1 && m.kmax > 1)) continue;
             if (plan_smem(m, k, level) > PBS_SMEM_MAX) continue;
-            if (best < 0) best = (int)i;
-            else if (small_l && plans[best].meta.C * 2 == C && plan_smem(m, k, level) <= 115712 &&
-                     m.lra + m.lrb + m.lrf == 10)
-                best = (int)i;
+            bool dup = false;                      // one plan per cluster size
+            for (int j : out) dup |= (plans[j].meta.C == C);
+            if (!dup) out.push_back((int)i);
         }
-    return best;
+    return out;
 }
 
 struct PbsTables {
@@ -62,15 +64,19 @@ struct PbsTables {
 static std::mutex g_plan_mu;
 static std::map<std::pair<int, int>, PbsTables> g_tables;   // (device, plan index)
 
-static int get_plan(int n, int k, int N, int level, int base_log, const PbsPlanEntry** entry, PbsLaunchArgs* a) {
+static int get_plan(int n, int k, int N, int level, int base_log, int variant, const PbsPlanEntry** entry,
+                    PbsLaunchArgs* a) {
     static const std::vector<PbsPlanEntry> plans = all_plans();
     const int logN = ilog2_exact(N);
     if (logN < 8 || logN > 15) FHE_FAIL(2, "pbs: polynomial size %d unsupported (256..32768)", N);
     if (k < 1 || k > 3) FHE_FAIL(2, "pbs: glwe dimension %d unsupported (1..3)", k);
     if (level < 1 || level > 4 || base_log < 1 || level * base_log > 52)
         FHE_FAIL(2, "pbs: decomposition level=%d base_log=%d unsupported", level, base_log);
-    const int pi = choose_plan(N, k, level);
-    if (pi < 0) FHE_FAIL(3, "pbs: N=%d k=%d level=%d does not fit the on-chip layout", N, k, level);
+    const std::vector<int> fit = fitting_plans(N, k, level);
+    if (fit.empty()) FHE_FAIL(3, "pbs: N=%d k=%d level=%d does not fit the on-chip layout", N, k, level);
+    if (variant < 0 || variant >= (int)fit.size())
+        FHE_FAIL(2, "pbs: plan variant %d out of range (0..%d)", variant, (int)fit.size() - 1);
+    const int pi = fit[variant];
     const PbsPlanMeta& m = plans[pi].meta;
     int dev = 0;
     FHE_CUDA(cudaGetDevice(&dev));
@@ -131,6 +137,26 @@ static int get_plan(int n, int k, int N, int level, int base_log, const PbsPlanE
 
 static long long* g_prof_buf = nullptr;
 
+// position of natural frequency t of the M-point spectrum inside one (j, o) slice [C][RF][BUF/RF] of a plan
+static long plan_position(const PbsPlanMeta& m, long t) {
+    const int R1 = 1 << m.logR1, RA = 1 << m.lra, RB = 1 << m.lrb, RF = 1 << m.lrf;
+    const long L1 = (long)RA * RB * RF;
+    const long t1 = t % R1, t2 = t / R1;
+    const long mA = t2 % RA, mB = (t2 / RA) % RB, mF = t2 / ((long)RA * RB);
+    const long pl = mA * (L1 / RA) + mB * RF + mF;             // DIF: the first pass fixes the lowest digit
+    const long buf = (m.C > 1) ? L1 : ((long)R1 * L1);
+    const long rank = (m.C > 1) ? t1 : 0, local = (m.C > 1) ? pl : t1 * L1 + pl;
+    const long w = local / RF, r = local % RF;
+    return rank * buf + r * (buf / RF) + w;
+}
+
+__global__ void k_bsk_relayout(double2* __restrict__ dst, const double2* __restrict__ src,
+                               const int* __restrict__ map /* dst position -> src position */, long nslices, int M) {
+    for (long s = blockIdx.y; s < nslices; s += gridDim.y)
+        for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < M; p += gridDim.x * blockDim.x)
+            dst[s * M + p] = src[s * M + map[p]];
+}
+
 extern "C" {
 
 // development aid: device buffer of >= 16 int64 that k_pbs accumulates per-phase clock64() deltas
@@ -143,9 +169,53 @@ int fhe_pbs_set_profile(long long* dev_buf) {
 // cluster size (CTAs per ciphertext) the on-chip layout uses for these parameters, <0 if unsupported
 int fhe_pbs_cluster_size(int N, int k, int level) {
     static const std::vector<PbsPlanEntry> plans = all_plans();
-    if (ilog2_exact(N) < 8 || ilog2_exact(N) > 15 || k < 1 || k > 3 || level < 1 || level > 4) return -1;
-    const int pi = choose_plan(N, k, level);
-    return pi < 0 ? -1 : plans[pi].meta.C;
+    const std::vector<int> fit = fitting_plans(N, k, level);
+    return fit.empty() ? -1 : plans[fit[0]].meta.C;
+}
+
+// number of plan variants for these parameters (0 = unsupported); variant 0 is the throughput plan, higher
+// variants use larger clusters (lower latency per ciphertext, fewer ciphertexts in flight)
+int fhe_pbs_num_variants(int N, int k, int level) { return (int)fitting_plans(N, k, level).size(); }
+int fhe_pbs_variant_cluster_size(int N, int k, int level, int variant) {
+    static const std::vector<PbsPlanEntry> plans = all_plans();
+    const std::vector<int> fit = fitting_plans(N, k, level);
+    if (variant < 0 || variant >= (int)fit.size()) return -1;
+    return plans[fit[variant]].meta.C;
+}
+
+// how many ciphertexts variant `variant` bootstraps concurrently on the current device (one wave)
+int fhe_pbs_variant_capacity(int N, int k, int level, int variant) {
+    static const std::vector<PbsPlanEntry> plans = all_plans();
+    const std::vector<int> fit = fitting_plans(N, k, level);
+    if (variant < 0 || variant >= (int)fit.size()) return -1;
+    PbsGeom g = {};
+    g.k = k; g.level = level; g.N = N; g.J = (k + 1) * level;
+    return plans[fit[variant]].capacity(g);
+}
+
+// Fourier BSK of variant `src_variant` -> layout of `dst_variant` (same spectrum, different order)
+int fhe_bsk_relayout(double2* dst, const double2* src, int n, int k, int N, int level, int src_variant,
+                     int dst_variant, void* stream) {
+    static const std::vector<PbsPlanEntry> plans = all_plans();
+    const std::vector<int> fit = fitting_plans(N, k, level);
+    if (src_variant < 0 || dst_variant < 0 || src_variant >= (int)fit.size() || dst_variant >= (int)fit.size())
+        FHE_FAIL(2, "bsk_relayout: variant out of range");
+    const int M = N / 2;
+    std::vector<long> inv_src(M);
+    std::vector<int> map(M);
+    for (long t = 0; t < M; t++) inv_src[t] = plan_position(plans[fit[src_variant]].meta, t);
+    for (long t = 0; t < M; t++) map[plan_position(plans[fit[dst_variant]].meta, t)] = (int)inv_src[t];
+    int* d_map = nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    FHE_CUDA(cudaMallocAsync(&d_map, sizeof(int) * M, st));
+    FHE_CUDA(cudaMemcpyAsync(d_map, map.data(), sizeof(int) * M, cudaMemcpyHostToDevice, st));
+    FHE_CUDA(cudaStreamSynchronize(st));     // `map` is a host temporary
+    const long nslices = (long)n * (k + 1) * level * (k + 1);
+    dim3 grid((unsigned)((M + 255) / 256), (unsigned)(nslices < 4096 ? nslices : 4096));
+    k_bsk_relayout<<<grid, 256, 0, st>>>(dst, src, d_map, nslices, M);
+    FHE_CHECK_LAUNCH();
+    FHE_CUDA(cudaFreeAsync(d_map, st));
+    return 0;
 }
 
 // number of double2 elements of the Fourier BSK
@@ -153,11 +223,17 @@ long fhe_bsk_fourier_elems(int n, int k, int N, int level) {
     return (long)n * (k + 1) * level * (k + 1) * (N / 2);
 }
 
+int fhe_bsk_to_fourier_variant(double2* bsk_f, const u64* bsk_std, int n, int k, int N, int level, int base_log,
+                               int variant, void* stream);
 int fhe_bsk_to_fourier(double2* bsk_f, const u64* bsk_std, int n, int k, int N, int level, int base_log,
                        void* stream) {
+    return fhe_bsk_to_fourier_variant(bsk_f, bsk_std, n, k, N, level, base_log, 0, stream);
+}
+int fhe_bsk_to_fourier_variant(double2* bsk_f, const u64* bsk_std, int n, int k, int N, int level, int base_log,
+                               int variant, void* stream) {
     PbsLaunchArgs a = {};
     const PbsPlanEntry* e = nullptr;
-    int rc = get_plan(n, k, N, level, base_log, &e, &a);
+    int rc = get_plan(n, k, N, level, base_log, variant, &e, &a);
     if (rc) return rc;
     a.st = (cudaStream_t)stream;
     a.outF = bsk_f;
@@ -166,19 +242,25 @@ int fhe_bsk_to_fourier(double2* bsk_f, const u64* bsk_std, int n, int k, int N, 
     return e->bsk(a);
 }
 
-// out [B][kN+1], in [B][n+1] (small key), luts [T][(k+1)N] accumulators, lut_idx [B] or null
-int fhe_pbs_batch(u64* out, const u64* in, long B, const double2* bsk_f, const u64* luts,
-                  const int* lut_idx, int n, int k, int N, int level, int base_log, void* stream) {
+// out [B][kN+1], in [B][n+1] (small key), luts [T][(k+1)N] accumulators, lut_idx [B] or null;
+// bsk_f must be in the layout of `variant` (fhe_bsk_to_fourier produces variant 0)
+int fhe_pbs_batch_variant(u64* out, const u64* in, long B, const double2* bsk_f, const u64* luts,
+                          const int* lut_idx, int n, int k, int N, int level, int base_log, int variant,
+                          void* stream) {
     if (B < 0) FHE_FAIL(2, "pbs_batch: negative batch");
     if (B == 0) return 0;
     PbsLaunchArgs a = {};
     const PbsPlanEntry* e = nullptr;
-    int rc = get_plan(n, k, N, level, base_log, &e, &a);
+    int rc = get_plan(n, k, N, level, base_log, variant, &e, &a);
     if (rc) return rc;
     a.st = (cudaStream_t)stream;
     a.out = out; a.in = in; a.B = B; a.bskF = bsk_f; a.luts = luts; a.lut_idx = lut_idx; a.prof = g_prof_buf;
     a.g.prof = g_prof_buf;
     return e->pbs(a);
+}
+int fhe_pbs_batch(u64* out, const u64* in, long B, const double2* bsk_f, const u64* luts,
+                  const int* lut_idx, int n, int k, int N, int level, int base_log, void* stream) {
+    return fhe_pbs_batch_variant(out, in, B, bsk_f, luts, lut_idx, n, k, N, level, base_log, 0, stream);
 }
 
 // test hook: out[p] = a_small[p] * b_torus[p] in Z_2^64[X]/(X^N+1) through the fp64 FFT path
@@ -186,7 +268,7 @@ int fhe_debug_polymul(u64* out, const i64* a_small, const u64* b_torus, long npo
                       int level, void* stream) {
     PbsLaunchArgs a = {};
     const PbsPlanEntry* e = nullptr;
-    int rc = get_plan(1, k, N, level, 8, &e, &a);
+    int rc = get_plan(1, k, N, level, 8, 0, &e, &a);
     if (rc) return rc;
     a.st = (cudaStream_t)stream;
     a.pm_out = out; a.pm_a = a_small; a.pm_b = b_torus; a.npoly = npoly;

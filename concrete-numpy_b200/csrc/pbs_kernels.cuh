@@ -451,11 +451,12 @@ __device__ __forceinline__ void stage1_gather(const double2* src_buf, int j2, co
 // inverse of stage 1 when the sub-transform outputs were pushed into this CTA: chunk t1 of `recv` holds the
 // Q values CTA t1 computed for this CTA's j2 range (still in the senders' swizzle)
 template <class P>
-__device__ __forceinline__ void stage1_gather_local(const double2* recv, int q, const double2* T, const PbsGeom& g,
+__device__ __forceinline__ void stage1_gather_local(const double2* recv, int j2, const double2* T, const PbsGeom& g,
                                                     double2* z) {
     double2 v[P::R1];
+    const int off = SW(j2) & (P::Q - 1);     // the senders stored element j2 at SW(j2); chunks are 8-aligned
 #pragma unroll
-    for (int t1 = 0; t1 < P::R1; t1++) v[t1] = recv[(t1 << P::LOGQ) + SW(q)];
+    for (int t1 = 0; t1 < P::R1; t1++) v[t1] = recv[(t1 << P::LOGQ) + off];
 #pragma unroll
     for (int t1 = 0; t1 < P::R1; t1++) v[t1] = cmulc(v[t1], T[t1]);
     Dft<P::R1, true>::run(v);
@@ -738,7 +739,7 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
                         mbar_wait(&s_bar_inv[o], inv_phase & 1);
                         o_ready = o;
                     }
-                    stage1_gather_local<P>(work + ((size_t)(k + 1 + o) << P::LOGBUF), q, T, g, z);
+                    stage1_gather_local<P>(work + ((size_t)(k + 1 + o) << P::LOGBUF), j2, T, g, z);
                 } else
                     stage1_gather<P>(work + ((size_t)o << P::LOGBUF), j2, T, g, z);
                 u64* acco = acc + ((size_t)o << P::LOGS);
@@ -957,6 +958,35 @@ struct PbsPlanOps {
     static size_t smem_pbs(const PbsGeom& g) {
         return (size_t)(g.k + 1) * P::S * 8 + (size_t)g.J * P::BUF * 16 + (size_t)P::TW_SMEM * 16;
     }
+    // ciphertexts (clusters) that can be resident at once for this geometry, or < 0 on error
+    static int capacity(const PbsGeom& g) {
+        const size_t smem = smem_pbs(g);
+        if (cudaFuncSetAttribute(k_pbs<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        if (P::C > 1) {
+            if (P::C > 8) cudaFuncSetAttribute(k_pbs<P>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            cudaLaunchConfig_t cfg = {};
+            cfg.blockDim = dim3(P::NT);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = P::C;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            cfg.gridDim = dim3(P::C * (sms / P::C));
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, k_pbs<P>, &cfg) != cudaSuccess) return -1;
+            return n;
+        }
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pbs<P>, P::NT, smem) != cudaSuccess) return -1;
+        if (per_sm > 512 / P::TM_CTA) per_sm = 512 / P::TM_CTA;
+        return per_sm * sms;
+    }
     static int pbs(const PbsLaunchArgs& a) {
         return launch_clustered(k_pbs<P>, P::C, P::NT, P::TM_CTA, smem_pbs(a.g), a.B, a.st, a.out, a.in, a.B, a.bskF, a.luts,
                                 a.lut_idx, a.g, a.twT, a.tw_mid, a.prof);
@@ -975,11 +1005,12 @@ struct PbsPlanOps {
 
 struct PbsPlanEntry {
     PbsPlanMeta meta;
+    int (*capacity)(const PbsGeom&);
     int (*pbs)(const PbsLaunchArgs&);
     int (*bsk)(const PbsLaunchArgs&);
     int (*polymul)(const PbsLaunchArgs&);
 };
 
 #define PBS_PLAN_ENTRY(...) \
-    PbsPlanEntry { PbsPlanOps<__VA_ARGS__>::meta(), &PbsPlanOps<__VA_ARGS__>::pbs, &PbsPlanOps<__VA_ARGS__>::bsk, \
+    PbsPlanEntry { PbsPlanOps<__VA_ARGS__>::meta(), &PbsPlanOps<__VA_ARGS__>::capacity, &PbsPlanOps<__VA_ARGS__>::pbs, &PbsPlanOps<__VA_ARGS__>::bsk, \
                    &PbsPlanOps<__VA_ARGS__>::polymul }

@@ -117,12 +117,48 @@ def bsk_std_to_fourier(bsk_std: torch.Tensor, p: CryptoParams) -> torch.Tensor:
 
 
 class EvalKeys:
-    """Evaluation keys only (what the server sees): Fourier BSK + KSK."""
+    """Evaluation keys only (what the server sees): Fourier BSK + KSK.
+
+    The bootstrap has several plan variants per parameter set (csrc/pbs.cu): variant 0 maximises the
+    ciphertexts in flight, higher variants use larger clusters per ciphertext.  A small batch (a step of a
+    sequential circuit) is run on the largest cluster size that still bootstraps the whole batch at once;
+    the Fourier BSK is permuted into that variant's layout on first use and cached."""
 
     def __init__(self, params: CryptoParams, bsk_f: torch.Tensor, ksk: torch.Tensor):
         self.params = params
         self.bsk_f = bsk_f
         self.ksk = ksk
+        self._variants = {0: bsk_f}
+        lib = _lib.load()
+        n = lib.fhe_pbs_num_variants(params.N, params.k, params.pbs_level)
+        self.variant_clusters = [lib.fhe_pbs_variant_cluster_size(params.N, params.k, params.pbs_level, v)
+                                 for v in range(max(n, 0))]
+        self._capacity = None      # ciphertexts each variant bootstraps in one wave (queried on the device)
+
+    def variant_for_batch(self, count: int) -> int:
+        """Largest-cluster variant that still bootstraps `count` ciphertexts in a single wave."""
+        if self._capacity is None:
+            lib = _lib.load()
+            p = self.params
+            with torch.cuda.device(self.bsk_f.device):
+                self._capacity = [lib.fhe_pbs_variant_capacity(p.N, p.k, p.pbs_level, v)
+                                  for v in range(len(self.variant_clusters))]
+        best = 0
+        for v, cap in enumerate(self._capacity):
+            # 16-CTA clusters are a capacity fallback (N = 32768 with >= 3 levels), not a latency win
+            if v > 0 and 0 < count <= cap and self.variant_clusters[v] <= 8:
+                best = v
+        return best
+
+    def bsk_for_variant(self, v: int) -> torch.Tensor:
+        if v not in self._variants:
+            p = self.params
+            out = torch.empty_like(self.bsk_f)
+            with torch.cuda.device(self.bsk_f.device):
+                _lib.call("fhe_bsk_relayout", out.data_ptr(), self.bsk_f.data_ptr(), p.n, p.k, p.N, p.pbs_level,
+                          0, v, _stream())
+            self._variants[v] = out
+        return self._variants[v]
 
     @staticmethod
     def of(keyset: KeySet) -> "EvalKeys":
@@ -214,19 +250,24 @@ def keyswitch(ev: EvalKeys, ct: torch.Tensor) -> torch.Tensor:
 
 
 def pbs_launch(ev: EvalKeys, out: torch.Tensor, ct_small: torch.Tensor, count: int, luts: torch.Tensor,
-               lut_idx: Optional[torch.Tensor]) -> None:
-    """One fhe_pbs_batch launch on the current stream: `count` ciphertexts from `ct_small` into `out`."""
+               lut_idx: Optional[torch.Tensor], variant: Optional[int] = None) -> None:
+    """One bootstrap launch on the current stream: `count` ciphertexts from `ct_small` into `out`."""
     p = ev.params
-    _lib.call("fhe_pbs_batch", out.data_ptr(), ct_small.data_ptr(), count, ev.bsk_f.data_ptr(),
-              luts.data_ptr(), _ptr(lut_idx), p.n, p.k, p.N, p.pbs_level, p.pbs_base_log, _stream())
+    v = ev.variant_for_batch(count) if variant is None else int(variant)
+    _lib.call("fhe_pbs_batch_variant", out.data_ptr(), ct_small.data_ptr(), count, ev.bsk_for_variant(v).data_ptr(),
+              luts.data_ptr(), _ptr(lut_idx), p.n, p.k, p.N, p.pbs_level, p.pbs_base_log, v, _stream())
 
 
-def bootstrap(ev: EvalKeys, ct_small: torch.Tensor, luts: torch.Tensor, lut_idx: Optional[torch.Tensor]) -> torch.Tensor:
+def bootstrap(ev: EvalKeys, ct_small: torch.Tensor, luts: torch.Tensor, lut_idx: Optional[torch.Tensor],
+              variant: Optional[int] = None) -> torch.Tensor:
     p = ev.params
     E = ct_small.numel() // (p.n + 1)
     out = torch.empty((E, p.ct_words), dtype=torch.int64, device=ct_small.device)
     with torch.cuda.device(ct_small.device):
-        pbs_launch(ev, out, ct_small, E, luts, lut_idx)
+        if variant is None:
+            pbs_launch(ev, out, ct_small, E, luts, lut_idx)
+        else:
+            pbs_launch(ev, out, ct_small, E, luts, lut_idx, variant)
     return out
 
 

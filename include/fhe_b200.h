@@ -75,6 +75,22 @@ int fhe_pbs_batch(uint64_t* out /* [B][kN+1] */, const uint64_t* in /* [B][n+1] 
                   const int* lut_idx /* [B] or NULL */, int n, int k, int N, int level, int base_log,
                   void* stream);
 
+/* Plan variants of the bootstrap: variant 0 is the throughput plan (smallest cluster, what
+ * fhe_bsk_to_fourier / fhe_pbs_batch use); higher variants spread one ciphertext over larger clusters and
+ * are meant for small batches (sequential circuits).  The Fourier BSK layout depends on the variant:
+ * fhe_bsk_relayout permutes a key from one variant's layout into another's (same spectrum values). */
+int fhe_pbs_num_variants(int N, int k, int level);
+int fhe_pbs_variant_cluster_size(int N, int k, int level, int variant);
+/* ciphertexts the variant bootstraps concurrently on the current device (one wave of clusters) */
+int fhe_pbs_variant_capacity(int N, int k, int level, int variant);
+int fhe_bsk_to_fourier_variant(void* bsk_f, const uint64_t* bsk_std, int n, int k, int N, int level,
+                               int base_log, int variant, void* stream);
+int fhe_bsk_relayout(void* dst_bsk_f, const void* src_bsk_f, int n, int k, int N, int level,
+                     int src_variant, int dst_variant, void* stream);
+int fhe_pbs_batch_variant(uint64_t* out, const uint64_t* in, long B, const void* bsk_f,
+                          const uint64_t* luts, const int* lut_idx, int n, int k, int N, int level,
+                          int base_log, int variant, void* stream);
+
 /* development aid: k_pbs accumulates per-phase clock64() deltas of one CTA into dev_buf[0..15]
  * (NULL switches it off); not part of the reference-facing surface */
 int fhe_pbs_set_profile(long long* dev_buf);

@@ -166,6 +166,36 @@ def test_pbs_matches_oracle(oracle, cuda_device, p_bits, n, k, N, level, base_lo
     assert err_gpu.std() <= 2.0 * err_ref.std() + 2.0 ** 20, (err_gpu.std(), err_ref.std())
 
 
+@pytest.mark.parametrize("p_bits,n,k,N,level,base_log", [(3, 16, 1, 1024, 2, 10), (4, 20, 1, 2048, 1, 23),
+                                                       (5, 16, 1, 4096, 2, 13), (6, 12, 1, 8192, 2, 13),
+                                                       (7, 8, 1, 16384, 2, 15), (8, 8, 1, 32768, 2, 15)])
+def test_pbs_plan_variants_agree(cuda_device, p_bits, n, k, N, level, base_log):
+    """Every plan variant (cluster size) of a parameter set bootstraps to the same messages from the
+    Fourier BSK permuted into its layout (fhe_bsk_relayout), with the same noise level."""
+    p = E.CryptoParams(p=p_bits, n=n, k=k, N=N, pbs_level=level, pbs_base_log=base_log, ks_level=8,
+                       ks_base_log=3, lwe_std=2.0 ** -40, glwe_std=2.0 ** -55)
+    ks = E.KeySet(p, cuda_device, seed=9)
+    ev = E.EvalKeys.of(ks)
+    assert len(ev.variant_clusters) >= 2 and ev.variant_clusters[0] == _lib.load().fhe_pbs_cluster_size(N, k, level)
+    rng = np.random.default_rng(N + 1)
+    B = 9
+    m = rng.integers(0, 1 << p_bits, B).astype(np.uint64)
+    table = rng.integers(0, 1 << p_bits, (1, 1 << p_bits))
+    luts = E.from_np_u64(E.build_lut_accumulators(p, table), cuda_device)
+    small = E.keyswitch(ev, E.encrypt(ks, m))
+    exp = table[0, m.astype(np.int64)].astype(np.uint64)
+    stds = []
+    for v in range(len(ev.variant_clusters)):
+        out = E.bootstrap(ev, small, luts, None, variant=v)
+        got, ph = E.decrypt(ks, out, return_phase=True)
+        assert np.array_equal(got, exp), (v, ev.variant_clusters[v])
+        stds.append((ph - (exp << np.uint64(63 - p_bits))).view(np.int64).astype(np.float64).std())
+    assert max(stds) <= 2.0 * min(stds) + 2.0 ** 20, stds
+    best = max(v for v, c in enumerate(ev.variant_clusters) if v == 0 or c <= 8)
+    assert ev.variant_for_batch(1) == best and ev.variant_for_batch(100000) == 0
+    assert all(c >= 1 for c in ev._capacity)
+
+
 def test_linear_ops_bit_exact(oracle, cuda_device):
     rng = np.random.default_rng(3)
     L = 2049
