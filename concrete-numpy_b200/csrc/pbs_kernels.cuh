@@ -577,13 +577,14 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
     constexpr int N = P::N, M = P::M;
     // optional phase timing (development aid, fhe_pbs_set_profile): thread 0 of CTA 0 accumulates
     // clock64() deltas per phase
-    const bool do_prof = (prof != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
+    // (CTA b < 16 writes prof[16*b + slot]: CTA 0 is the reference, the others show the skew inside cluster 0)
+    const bool do_prof = (prof != nullptr) && blockIdx.x < 16 && threadIdx.x == 0;
     long long t_last = do_prof ? clock64() : 0;
-#define PBS_PROF(slot)                         \
-    if (do_prof) {                             \
-        const long long t_now = clock64();     \
-        prof[slot] += t_now - t_last;          \
-        t_last = t_now;                        \
+#define PBS_PROF(slot)                                   \
+    if (do_prof) {                                       \
+        const long long t_now = clock64();               \
+        prof[16 * blockIdx.x + slot] += t_now - t_last;  \
+        t_last = t_now;                                  \
     }
     constexpr int NG = BUF / RF;                    // butterfly groups of the fused pass
     const int k = g.k, level = g.level, J = g.J, base_log = g.base_log;

@@ -91,7 +91,7 @@ int fhe_pbs_batch_variant(uint64_t* out, const uint64_t* in, long B, const void*
                           const uint64_t* luts, const int* lut_idx, int n, int k, int N, int level,
                           int base_log, int variant, void* stream);
 
-/* development aid: k_pbs accumulates per-phase clock64() deltas of one CTA into dev_buf[0..15]
+/* development aid: k_pbs accumulates per-phase clock64() deltas of CTA b < 16 into dev_buf[16*b .. 16*b+15]
  * (NULL switches it off); not part of the reference-facing surface */
 int fhe_pbs_set_profile(long long* dev_buf);
 

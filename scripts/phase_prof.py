@@ -19,7 +19,7 @@ for pbits, B in ((8, 36), (6, 148), (4, 888)):
     luts = E.from_np_u64(E.build_lut_accumulators(p, table), dev)
     small = E.keyswitch(ev, E.encrypt(ks, m))
     E.bootstrap(ev, small, luts, None)
-    prof = torch.zeros(16, dtype=torch.int64, device=dev)
+    prof = torch.zeros(256, dtype=torch.int64, device=dev)
     _lib.call("fhe_pbs_set_profile", prof.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -35,6 +35,12 @@ for pbits, B in ((8, 36), (6, 148), (4, 888)):
           f"=> {c.sum() / (ms * 1e-3) / 1e6:.0f} MHz")
     for nm, v in zip(NAMES, c):
         print(f"   {nm:18s} {v / max(c.sum(), 1) * 100:5.1f}%   {v / 1e3:10.0f} kcycles")
+    allp = prof.cpu().numpy().reshape(16, 16).astype(np.float64)
+    C = max(1, _lib.load().fhe_pbs_cluster_size(p.N, p.k, p.pbs_level))
+    if C > 1:
+        print("   per-rank kcycles of cluster 0 (P1 | syncA | midF | fused | midI | syncB | P5 | syncC):")
+        for r in range(min(C, 16)):
+            print("     rank %2d: " % r + " ".join("%7.0f" % (allp[r, i] / 1e3) for i in range(8)))
     extra = prof.cpu().numpy()[9:11].astype(np.float64)
     print(f"   (thread 0 inside P1: loads+diff {extra[0] / 1e3:.0f} kcycles, level loop {extra[1] / 1e3:.0f} kcycles)")
     del ks, ev

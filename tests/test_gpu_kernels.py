@@ -124,6 +124,10 @@ PBS_CASES = [
     (4, 16, 1, 8192, 3, 10),
     (4, 8, 1, 32768, 3, 10),      # 16-CTA cluster plan (two clusters per SM)
     (3, 12, 1, 4096, 3, 10),      # 2-CTA cluster plan with 1024-point local transforms
+    (4, 16, 1, 2048, 3, 12),      # 36 kept bits: 64-bit decomposition state
+    (3, 12, 1, 1024, 4, 9),       # 4 levels
+    (3, 16, 2, 1024, 1, 18),      # k = 2 (radix-4 fused pass)
+    (3, 16, 3, 512, 1, 18),       # k = 3
 ]
 
 
