@@ -17,12 +17,14 @@ print(res, flush=True)
 SETS = {
     "p4": E.CryptoParams(p=4, n=742, k=1, N=2048, pbs_level=1, pbs_base_log=23, ks_level=5, ks_base_log=3,
                          lwe_std=7.0698e-6, glwe_std=2.9404e-16),
+    "p5": E.CryptoParams(p=5, n=786, k=1, N=4096, pbs_level=2, pbs_base_log=13, ks_level=5, ks_base_log=3,
+                         lwe_std=3.2e-6, glwe_std=2.168e-19),
     "p6": E.CryptoParams(p=6, n=864, k=1, N=8192, pbs_level=2, pbs_base_log=15, ks_level=6, ks_base_log=3,
                          lwe_std=7.58e-7, glwe_std=2.168e-19),
     "p8": E.CryptoParams(p=8, n=996, k=1, N=32768, pbs_level=2, pbs_base_log=15, ks_level=7, ks_base_log=3,
                          lwe_std=6.7677e-8, glwe_std=2.168e-19),
 }
-BATCH = {"p4": 4096, "p6": 1024, "p8": 256}
+BATCH = {"p4": 4096, "p5": 2048, "p6": 1024, "p8": 256}
 
 
 def flops_pbs(p):
