@@ -6,6 +6,7 @@ Ciphertext tensors are `torch.int64` of shape `[E, k*N+1]` (bit pattern of the u
 mask first, body last) -- SURVEY.md Appendix A.1.
 """
 
+import os
 from dataclasses import asdict, dataclass
 from typing import Optional
 
@@ -272,8 +273,12 @@ def bootstrap(ev: EvalKeys, ct_small: torch.Tensor, luts: torch.Tensor, lut_idx:
 
 
 _SIDE_STREAMS = {}
+# Two-stream keyswitch/bootstrap pipelining is opt-in (CNP_B200_PIPELINE=1): measured on B200 it hides the
+# keyswitch (share of the bootstrap in a step 0.93 -> 0.96) but the concurrent keyswitch slows the bootstrap
+# by about as much (L2/HBM contention) and chunking adds partial waves, so the net effect is within the
+# box-to-box noise (+0.7 % / -2 % in two runs).
 PIPELINE_MIN_CHUNK = 480          # ciphertexts; below 2 chunks of this size the lookup is not pipelined
-PIPELINE_MAX_CHUNKS = 4
+PIPELINE_MAX_CHUNKS = 4 if os.environ.get("CNP_B200_PIPELINE", "0") not in ("", "0") else 1
 
 
 def _side_stream(device) -> "torch.cuda.Stream":
