@@ -359,8 +359,7 @@ __device__ __forceinline__ void mid_pass(double2* __restrict__ work, int nbuf, u
         static_assert(WPT == 1, "twiddles are per-thread constants");
         constexpr int TMW = (4 * (R - 1) <= 4) ? 4 : (4 * (R - 1) <= 16) ? 16 : (4 * (R - 1) <= 32) ? 32 : 64;
         double2 t[TMW / 4 + 1];
-        if (TM) tmem_load_c<TMW / 4>(tw_taddr, t + 1);
-        else {
+        if (!TM) {
 #pragma unroll
             for (int m = 1; m < R; m++) t[m] = tw[((m - 1) << LOGSS) + q];
         }
@@ -372,9 +371,13 @@ __device__ __forceinline__ void mid_pass(double2* __restrict__ work, int nbuf, u
             for (int r = 0; r < R; r++) x[r] = base[SW(pos0 + (r << LOGSS))];
             if (!INV) {
                 Dft<R, false>::run(x);
+                // tensor-memory twiddles are re-read per buffer right where they are needed: a ~75-cycle load
+                // is cheaper than 64 registers held across the butterfly
+                if (TM) tmem_load_c<TMW / 4>(tw_taddr, t + 1);
 #pragma unroll
                 for (int m = 1; m < R; m++) x[m] = cmul(x[m], t[m]);
             } else {
+                if (TM) tmem_load_c<TMW / 4>(tw_taddr, t + 1);
 #pragma unroll
                 for (int m = 1; m < R; m++) x[m] = cmulc(x[m], t[m]);
                 Dft<R, true>::run(x);
