@@ -25,6 +25,11 @@ _SIGS = {
     "fhe_trivial_lwe_batch": (C.c_int, [_p, _p, C.c_long, C.c_int, _p]),
     "fhe_decrypt_lwe_batch": (C.c_int, [_p, _p, _p, C.c_long, _p, C.c_int, C.c_int, _p]),
     "fhe_keyswitch_batch": (C.c_int, [_p, _p, C.c_long, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
+    "fhe_ks_tc_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fhe_ksk_tc_bytes": (C.c_long, [C.c_int, C.c_int, C.c_int]),
+    "fhe_keyswitch_tc_scratch_bytes": (C.c_long, [C.c_long, C.c_int, C.c_int]),
+    "fhe_ksk_to_tc": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p]),
+    "fhe_keyswitch_batch_tc": (C.c_int, [_p, _p, C.c_long, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_pbs_cluster_size": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "fhe_bsk_fourier_elems": (C.c_long, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "fhe_bsk_to_fourier": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),

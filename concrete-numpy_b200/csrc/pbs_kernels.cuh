@@ -359,10 +359,14 @@ __device__ __forceinline__ void mid_pass(double2* __restrict__ work, int nbuf, u
         static_assert(WPT == 1, "twiddles are per-thread constants");
         constexpr int TMW = (4 * (R - 1) <= 4) ? 4 : (4 * (R - 1) <= 16) ? 16 : (4 * (R - 1) <= 32) ? 32 : 64;
         double2 t[TMW / 4 + 1];
+        // tcgen05.ld is warp-collective: it may sit inside the buffer loop only when the thread groups are
+        // whole warps (otherwise part of a warp would skip it -- that hung the k = 2, N = 256 plan)
+        constexpr bool TM_IN_LOOP = TM && (NBF % 32 == 0);
         if (!TM) {
 #pragma unroll
             for (int m = 1; m < R; m++) t[m] = tw[((m - 1) << LOGSS) + q];
-        }
+        } else if (!TM_IN_LOOP)
+            tmem_load_c<TMW / 4>(tw_taddr, t + 1);
 #pragma unroll 1
         for (int buf = grp; buf < nbuf; buf += GROUPS) {
             double2* base = work + ((size_t)buf << LOGBUF);
@@ -373,11 +377,11 @@ __device__ __forceinline__ void mid_pass(double2* __restrict__ work, int nbuf, u
                 Dft<R, false>::run(x);
                 // tensor-memory twiddles are re-read per buffer right where they are needed: a ~75-cycle load
                 // is cheaper than 64 registers held across the butterfly
-                if (TM) tmem_load_c<TMW / 4>(tw_taddr, t + 1);
+                if (TM_IN_LOOP) tmem_load_c<TMW / 4>(tw_taddr, t + 1);
 #pragma unroll
                 for (int m = 1; m < R; m++) x[m] = cmul(x[m], t[m]);
             } else {
-                if (TM) tmem_load_c<TMW / 4>(tw_taddr, t + 1);
+                if (TM_IN_LOOP) tmem_load_c<TMW / 4>(tw_taddr, t + 1);
 #pragma unroll
                 for (int m = 1; m < R; m++) x[m] = cmulc(x[m], t[m]);
                 Dft<R, true>::run(x);

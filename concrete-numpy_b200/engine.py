@@ -135,6 +135,19 @@ class EvalKeys:
         self.variant_clusters = [lib.fhe_pbs_variant_cluster_size(params.N, params.k, params.pbs_level, v)
                                  for v in range(max(n, 0))]
         self._capacity = None      # ciphertexts each variant bootstraps in one wave (queried on the device)
+        # tensor-core keyswitch (csrc/keyswitch_tc.cu): key bytes re-laid out once, on first use
+        self.ks_tc_ok = bool(lib.fhe_ks_tc_supported(params.big_dim, params.n, params.ks_level, params.ks_base_log))
+        self._ksk_tc = None
+
+    def ksk_tc(self) -> torch.Tensor:
+        if self._ksk_tc is None:
+            p = self.params
+            lib = _lib.load()
+            buf = torch.empty(lib.fhe_ksk_tc_bytes(p.big_dim, p.n, p.ks_level), dtype=torch.uint8, device=self.ksk.device)
+            with torch.cuda.device(self.ksk.device):
+                _lib.call("fhe_ksk_to_tc", buf.data_ptr(), self.ksk.data_ptr(), p.big_dim, p.n, p.ks_level, _stream())
+            self._ksk_tc = buf
+        return self._ksk_tc
 
     def variant_for_batch(self, count: int) -> int:
         """Largest-cluster variant that still bootstraps `count` ciphertexts in a single wave."""
@@ -239,14 +252,30 @@ def build_lut_accumulators(params: CryptoParams, tables: np.ndarray) -> np.ndarr
     return out
 
 
+def keyswitch_launch(ev: EvalKeys, out: torch.Tensor, ct: torch.Tensor, count: int) -> None:
+    """Keyswitch `count` ciphertexts of `ct` into `out` on the current stream: int8-limb GEMM on the tensor
+    cores when the parameters allow it exactly (bit-identical results), else the CUDA-core kernel."""
+    p = ev.params
+    if count <= 0:
+        return
+    if ev.ks_tc_ok and os.environ.get("CNP_B200_KS_TC", "1") not in ("", "0"):
+        lib = _lib.load()
+        scratch = torch.empty(lib.fhe_keyswitch_tc_scratch_bytes(count, p.big_dim, p.ks_level), dtype=torch.uint8,
+                              device=ct.device)
+        _lib.call("fhe_keyswitch_batch_tc", out.data_ptr(), ct.data_ptr(), count, ev.ksk_tc().data_ptr(),
+                  scratch.data_ptr(), p.big_dim, p.n, p.ks_level, p.ks_base_log, _stream())
+    else:
+        _lib.call("fhe_keyswitch_batch", out.data_ptr(), ct.data_ptr(), count, ev.ksk.data_ptr(), p.big_dim,
+                  p.n, p.ks_level, p.ks_base_log, _stream())
+
+
 def keyswitch(ev: EvalKeys, ct: torch.Tensor) -> torch.Tensor:
     p = ev.params
     ct = ct.contiguous()
     E = ct.numel() // p.ct_words
     out = torch.empty((E, p.n + 1), dtype=torch.int64, device=ct.device)
     with torch.cuda.device(ct.device):
-        _lib.call("fhe_keyswitch_batch", out.data_ptr(), ct.data_ptr(), E, ev.ksk.data_ptr(), p.big_dim,
-                  p.n, p.ks_level, p.ks_base_log, _stream())
+        keyswitch_launch(ev, out, ct, E)
     return out
 
 
@@ -311,8 +340,7 @@ def table_lookup(ev: EvalKeys, ct: torch.Tensor, luts: torch.Tensor, lut_idx: Op
 
     def ks(i):
         lo, hi = bounds[i], bounds[i + 1]
-        _lib.call("fhe_keyswitch_batch", small[lo:hi].data_ptr(), ct[lo:hi].data_ptr(), hi - lo, ev.ksk.data_ptr(),
-                  p.big_dim, p.n, p.ks_level, p.ks_base_log, _stream())
+        keyswitch_launch(ev, small[lo:hi], ct[lo:hi], hi - lo)
 
     def pbs(i):
         lo, hi = bounds[i], bounds[i + 1]

@@ -70,6 +70,16 @@ int fhe_decrypt_lwe_batch(uint64_t* phase, uint64_t* msg, const uint64_t* ct, lo
  * (concrete/numpy/mlir/node_converter.py:1190-1206). */
 int fhe_keyswitch_batch(uint64_t* out /* [B][n+1] */, const uint64_t* in /* [B][kN+1] */, long B,
                         const uint64_t* ksk, int kN, int n, int level, int base_log, void* stream);
+/* Tensor-core keyswitch (csrc/keyswitch_tc.cu): the same contraction as an int8 x uint8 -> int32 GEMM on
+ * tcgen05 (8 byte limbs per key word), bit-exact; usable when fhe_ks_tc_supported() (digits fit int8 and no
+ * int32 limb sum can overflow).  The key is re-laid out once (fhe_ksk_to_tc), the digits of a batch go to a
+ * caller-provided scratch buffer of fhe_keyswitch_tc_scratch_bytes(). */
+int fhe_ks_tc_supported(int kN, int n, int level, int base_log);
+long fhe_ksk_tc_bytes(int kN, int n, int level);
+long fhe_keyswitch_tc_scratch_bytes(long B, int kN, int level);
+int fhe_ksk_to_tc(void* ksk_tc, const uint64_t* ksk, int kN, int n, int level, void* stream);
+int fhe_keyswitch_batch_tc(uint64_t* out, const uint64_t* in, long B, const void* ksk_tc, void* scratch,
+                           int kN, int n, int level, int base_log, void* stream);
 int fhe_pbs_batch(uint64_t* out /* [B][kN+1] */, const uint64_t* in /* [B][n+1] */, long B,
                   const void* bsk_f, const uint64_t* luts /* [T][(k+1)N] accumulators */,
                   const int* lut_idx /* [B] or NULL */, int n, int k, int N, int level, int base_log,

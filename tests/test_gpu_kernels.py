@@ -131,6 +131,27 @@ PBS_CASES = [
 ]
 
 
+@pytest.mark.parametrize("B,kN,n,level,base_log", [(1, 256, 31, 2, 4), (37, 512, 48, 4, 4), (130, 1024, 97, 5, 3),
+                                                   (300, 2048, 130, 2, 7), (129, 4096, 500, 8, 2)])
+def test_keyswitch_tensor_core_bit_exact(oracle, cuda_device, B, kN, n, level, base_log):
+    """The tcgen05 int8-limb GEMM keyswitch (csrc/keyswitch_tc.cu) equals the oracle bit for bit."""
+    lib = _lib.load()
+    assert lib.fhe_ks_tc_supported(kN, n, level, base_log) == 1
+    assert lib.fhe_ks_tc_supported(kN, n, level, 9) == 0            # digits no longer fit int8
+    rng = np.random.default_rng(B * 7 + kN)
+    ksk = rng.integers(0, 1 << 64, (kN, level, n + 1), dtype=np.uint64)
+    ct = rng.integers(0, 1 << 64, (B, kN + 1), dtype=np.uint64)
+    d_ksk, d_ct = E.from_np_u64(ksk, cuda_device), E.from_np_u64(ct, cuda_device)
+    st = torch.cuda.current_stream().cuda_stream
+    ksk_tc = torch.empty(lib.fhe_ksk_tc_bytes(kN, n, level), dtype=torch.uint8, device=cuda_device)
+    _lib.call("fhe_ksk_to_tc", ksk_tc.data_ptr(), d_ksk.data_ptr(), kN, n, level, st)
+    scratch = torch.empty(lib.fhe_keyswitch_tc_scratch_bytes(B, kN, level), dtype=torch.uint8, device=cuda_device)
+    out = torch.empty((B, n + 1), dtype=torch.int64, device=cuda_device)
+    _lib.call("fhe_keyswitch_batch_tc", out.data_ptr(), d_ct.data_ptr(), B, ksk_tc.data_ptr(), scratch.data_ptr(),
+              kN, n, level, base_log, st)
+    assert np.array_equal(E.to_np_u64(out), oracle.keyswitch(ct, ksk, level, base_log))
+
+
 @pytest.mark.parametrize("p_bits,n,k,N,level,base_log", PBS_CASES)
 def test_pbs_matches_oracle(oracle, cuda_device, p_bits, n, k, N, level, base_log):
     p = E.CryptoParams(p=p_bits, n=n, k=k, N=N, pbs_level=level, pbs_base_log=base_log, ks_level=8,
