@@ -502,7 +502,9 @@ __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* _
     const ST mask = (ST)((1ULL << base_log) - 1);
     const int nonrep = 64 - level * base_log;
     const bool do_prof = (g.prof != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
-#pragma unroll 1
+    // small stage-1 radices mean many light items per thread: unroll them for instruction-level parallelism
+    constexpr int ITEM_UNROLL = (R1 <= 2) ? 4 : (R1 <= 4) ? 2 : 1;
+#pragma unroll ITEM_UNROLL
     for (int it = threadIdx.x; it < ((k + 1) << P::LOGQ); it += NT) {
         const long long t_a = do_prof ? clock64() : 0;
         const int c = it >> P::LOGQ, q = it & (Q - 1);

@@ -260,10 +260,17 @@ def keyswitch_launch(ev: EvalKeys, out: torch.Tensor, ct: torch.Tensor, count: i
         return
     if ev.ks_tc_ok and os.environ.get("CNP_B200_KS_TC", "1") not in ("", "0"):
         lib = _lib.load()
-        scratch = torch.empty(lib.fhe_keyswitch_tc_scratch_bytes(count, p.big_dim, p.ks_level), dtype=torch.uint8,
-                              device=ct.device)
-        _lib.call("fhe_keyswitch_batch_tc", out.data_ptr(), ct.data_ptr(), count, ev.ksk_tc().data_ptr(),
-                  scratch.data_ptr(), p.big_dim, p.n, p.ks_level, p.ks_base_log, _stream())
+        ksk_tc = ev.ksk_tc()
+        # the digit matrix of a chunk (rows x level*kN bytes) is kept under ~1 GiB
+        rows = max(128, ((1 << 30) // max(lib.fhe_keyswitch_tc_scratch_bytes(128, p.big_dim, p.ks_level), 1)) * 128)
+        out2 = out.view(-1, p.n + 1)
+        ct2 = ct.view(-1, p.ct_words)
+        for lo in range(0, count, rows):
+            hi = min(count, lo + rows)
+            scratch = torch.empty(lib.fhe_keyswitch_tc_scratch_bytes(hi - lo, p.big_dim, p.ks_level), dtype=torch.uint8,
+                                  device=ct.device)
+            _lib.call("fhe_keyswitch_batch_tc", out2[lo:hi].data_ptr(), ct2[lo:hi].data_ptr(), hi - lo, ksk_tc.data_ptr(),
+                      scratch.data_ptr(), p.big_dim, p.n, p.ks_level, p.ks_base_log, _stream())
     else:
         _lib.call("fhe_keyswitch_batch", out.data_ptr(), ct.data_ptr(), count, ev.ksk.data_ptr(), p.big_dim,
                   p.n, p.ks_level, p.ks_base_log, _stream())
