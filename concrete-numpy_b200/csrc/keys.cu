@@ -149,7 +149,9 @@ __global__ void k_bsk_gadget(u64* __restrict__ bsk, const u64* __restrict__ sk_s
     const int r = (int)(R % (k + 1));
     const int lv = (int)((R / (k + 1)) % level);
     const long i = R / ((long)(k + 1) * level);
-    if (sk_small[i]) bsk[((size_t)R * (k + 1) + r) * N] += 1ULL << (64 - (lv + 1) * base_log);
+    // key entries are 0/1 for an LWE key; the extended key of the packing keyswitch (wide-integer path) also
+    // holds -1 for the body slot
+    bsk[((size_t)R * (k + 1) + r) * N] += sk_small[i] * (1ULL << (64 - (lv + 1) * base_log));
 }
 
 // compact list of set positions of each GLWE key polynomial (single CTA, serial scan is fine)

@@ -258,6 +258,37 @@ int fhe_pbs_batch_variant(u64* out, const u64* in, long B, const double2* bsk_f,
     a.g.prof = g_prof_buf;
     return e->pbs(a);
 }
+// Blind rotation with one GGSW list per ciphertext (wide-integer lookup, wide.py): ciphertext e uses the n Fourier
+// GGSWs at ggsw_f + e * ct_stride (double2 elements, variant-0 layout); `in` holds the rotation amounts as LWE masks.
+int fhe_blind_rotate_batch(u64* out, const u64* in, long B, const double2* ggsw_f, long ct_stride, const u64* luts,
+                           const int* lut_idx, int n, int k, int N, int level, int base_log, void* stream) {
+    if (B < 0 || ct_stride <= 0) FHE_FAIL(2, "blind_rotate_batch: bad arguments");
+    if (B == 0) return 0;
+    PbsLaunchArgs a = {};
+    const PbsPlanEntry* e = nullptr;
+    int rc = get_plan(n, k, N, level, base_log, 0, &e, &a);
+    if (rc) return rc;
+    a.st = (cudaStream_t)stream;
+    a.out = out; a.in = in; a.B = B; a.bskF = ggsw_f; a.luts = luts; a.lut_idx = lut_idx;
+    a.bsk_ct_stride = (size_t)ct_stride;
+    return e->pbs(a);
+}
+
+// out[b] = pool[i0[b]] + GGSW[gi[b]] (x) (pool[i1[b]] - pool[i0[b]]); pool [P][(k+1)N], out [B][(k+1)N],
+// ggsw_f: Fourier GGSWs in the variant-0 layout of (N, k, level) (fhe_bsk_to_fourier with n = their count)
+int fhe_cmux_batch(u64* out, const u64* pool, const int* i0, const int* i1, const double2* ggsw_f, const int* gi,
+                   long B, int k, int N, int level, int base_log, void* stream) {
+    if (B < 0) FHE_FAIL(2, "cmux_batch: negative batch");
+    if (B == 0) return 0;
+    PbsLaunchArgs a = {};
+    const PbsPlanEntry* e = nullptr;
+    int rc = get_plan(1, k, N, level, base_log, 0, &e, &a);
+    if (rc) return rc;
+    a.st = (cudaStream_t)stream;
+    a.out = out; a.B = B; a.bskF = ggsw_f; a.cm_pool = pool; a.cm_i0 = i0; a.cm_i1 = i1; a.cm_gi = gi;
+    return e->cmux(a);
+}
+
 int fhe_pbs_batch(u64* out, const u64* in, long B, const double2* bsk_f, const u64* luts,
                   const int* lut_idx, int n, int k, int N, int level, int base_log, void* stream) {
     return fhe_pbs_batch_variant(out, in, B, bsk_f, luts, lut_idx, n, k, N, level, base_log, 0, stream);

@@ -576,11 +576,13 @@ __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* _
 }
 
 // ---- the bootstrap kernel ------------------------------------------------------------------
-template <class P>
+// PERCT: every ciphertext brings its own list of n Fourier GGSWs (bsk_ct_stride double2 apart) -- the blind
+// rotation of the wide-integer lookup, where the GGSWs come out of circuit bootstrapping (wide.py)
+template <class P, bool PERCT = false>
 __global__ void __launch_bounds__(P::NT, P::MINB)
-k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* __restrict__ bskF,
+k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* __restrict__ bskF_all,
       const u64* __restrict__ luts, const int* __restrict__ lut_idx, const PbsGeom g,
-      const double2* __restrict__ twT, const double2* __restrict__ tw_mid, long long* prof) {
+      const double2* __restrict__ twT, const double2* __restrict__ tw_mid, long long* prof, size_t bsk_ct_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int C = P::C, R1 = P::R1, NT = P::NT, RF = P::RF, BUF = P::BUF, Q = P::Q, S = P::S;
     constexpr int N = P::N, M = P::M;
@@ -626,6 +628,7 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
     }
 
     for (long ct = cluster_id; ct < B; ct += nclusters) {
+        const double2* bskF = PERCT ? bskF_all + (size_t)ct * bsk_ct_stride : bskF_all;
         const u64* lwe = in + (size_t)ct * (g.n + 1);
         const u64* lut = luts + (size_t)(lut_idx ? lut_idx[ct] : 0) * (k + 1) * N;
         // ---- ACC = X^{-b~} * LUT
@@ -907,6 +910,108 @@ k_polymul_test(u64* __restrict__ out, const i64* __restrict__ a_small, const u64
     tw_teardown<P>(tw);
 }
 
+// ---- batched CMUX on GLWE ciphertexts (selection tree of the wide-integer lookup) ------------------
+//   out[b] = pool[i0[b]] + GGSW[gi[b]] (x) (pool[i1[b]] - pool[i0[b]])
+// pool: [P][(k+1)N] u64 (plaintext polynomials are trivial GLWEs), GGSWs in the Fourier layout of this plan
+// (fhe_bsk_to_fourier with n = number of GGSWs).  One external product per work item: a few per lookup next
+// to the ~10^5 of its bootstraps, so this kernel favours reuse of the bootstrap's phases over tuning.
+template <class P>
+__global__ void __launch_bounds__(P::NT, P::MINB)
+k_cmux(u64* __restrict__ out, const u64* __restrict__ pool, const int* __restrict__ i0, const int* __restrict__ i1,
+       const double2* __restrict__ ggswF, const int* __restrict__ gi, long B, const PbsGeom g,
+       const double2* __restrict__ twT, const double2* __restrict__ tw_mid) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int C = P::C, R1 = P::R1, NT = P::NT, RF = P::RF, BUF = P::BUF, N = P::N, M = P::M, Q = P::Q;
+    constexpr int NG = BUF / RF;
+    const int k = g.k, level = g.level, J = g.J, base_log = g.base_log;
+    double2* work = reinterpret_cast<double2*>(smem_raw);   // [J][BUF]
+    int rank = 0;
+    if (C > 1) rank = (int)cg::this_cluster().block_rank();
+    const long cluster_id = blockIdx.x / C, nclusters = gridDim.x / C;
+    const size_t glwe = (size_t)(k + 1) * N;
+    const size_t ggsw_stride = (size_t)J * (k + 1) * C * BUF;
+    const TwCtx tw = tw_setup<P>(work + (size_t)J * BUF, twT, tw_mid);
+    csync<C>();
+    for (long b = cluster_id; b < B; b += nclusters) {
+        const u64* d0 = pool + (size_t)i0[b] * glwe;
+        const u64* d1 = pool + (size_t)i1[b] * glwe;
+        const double2* gg = ggswF + (size_t)gi[b] * ggsw_stride;
+        for (int c = 0; c <= k; c++)
+            for (int lv = 0; lv < level; lv++)
+                forward_poly<P>(work, c * level + lv, rank, g, tw, [&](int coef) {
+                    int dg[16];
+                    signed_decompose<16>(d1[(size_t)c * N + coef] - d0[(size_t)c * N + coef], base_log, level, dg);
+                    int d = 0;
+#pragma unroll
+                    for (int t = 0; t < 16; t++) d = (t == level - 1 - lv) ? dg[t] : d;
+                    return (double)d;
+                });
+        csync<C>();
+        mid_passes<P, false>(work, J, tw);
+#pragma unroll 1
+        for (int w = threadIdx.x; w < NG; w += NT) {
+            double2 r[P::KMAX + 1][RF];
+#pragma unroll
+            for (int o = 0; o <= P::KMAX; o++)
+#pragma unroll
+                for (int m = 0; m < RF; m++) r[o][m] = make_double2(0.0, 0.0);
+            const double2* gp = gg + ((size_t)rank << P::LOGBUF) + w;
+            const size_t o_stride = (size_t)P::C << P::LOGBUF;
+#pragma unroll 1
+            for (int j = 0; j < J; j++) {
+                double2 x[RF];
+                const double2* base = work + ((size_t)j << P::LOGBUF);
+#pragma unroll
+                for (int m = 0; m < RF; m++) x[m] = base[SW(w * RF + m)];
+                Dft<RF, false>::run(x);
+                const double2* gj = gp + (size_t)j * (k + 1) * o_stride;
+#pragma unroll
+                for (int o = 0; o <= P::KMAX; o++)
+                    if (o <= k) {
+#pragma unroll
+                        for (int m = 0; m < RF; m++) {
+                            const double2 v = __ldg(gj + o * o_stride + m * NG);
+                            r[o][m].x = fma(x[m].x, v.x, r[o][m].x);
+                            r[o][m].x = fma(-x[m].y, v.y, r[o][m].x);
+                            r[o][m].y = fma(x[m].x, v.y, r[o][m].y);
+                            r[o][m].y = fma(x[m].y, v.x, r[o][m].y);
+                        }
+                    }
+            }
+#pragma unroll
+            for (int o = 0; o <= P::KMAX; o++)
+                if (o <= k) {
+                    Dft<RF, true>::run(r[o]);
+                    double2* base = work + ((size_t)o << P::LOGBUF);
+#pragma unroll
+                    for (int m = 0; m < RF; m++) base[SW(w * RF + m)] = r[o][m];
+                }
+        }
+        __syncthreads();
+        mid_passes<P, true>(work, k + 1, tw);
+        csync<C>();
+#pragma unroll 1
+        for (int it = threadIdx.x; it < ((k + 1) << P::LOGQ); it += NT) {
+            const int o = it >> P::LOGQ, q = it & (Q - 1);
+            const int j2 = (rank << P::LOGQ) + q;
+            double2 T[R1];
+            load_T<P>(T, tw, j2);
+            double2 z[R1];
+            stage1_gather<P>(work + ((size_t)o << P::LOGBUF), j2, T, g, z);
+            const u64* src = d0 + (size_t)o * N;
+            u64* dst = out + (size_t)b * glwe + (size_t)o * N;
+#pragma unroll
+            for (int j1 = 0; j1 < R1; j1++) {
+                const int c0 = (j1 << P::LOGL1) + j2;
+                dst[c0] = src[c0] + f2torus(z[j1].x * g.inv_M);
+                dst[M + c0] = src[M + c0] + f2torus(z[j1].y * g.inv_M);
+            }
+        }
+        csync<C>();
+    }
+    tw_teardown<P>(tw);
+}
+
 // ------------------------------------------------------------------ host launch helpers ----
 template <typename Kern, typename... Args>
 static int launch_clustered(Kern kern, int C, int NT, int tmem_cols, size_t smem, long work_items, cudaStream_t st,
@@ -953,6 +1058,9 @@ struct PbsLaunchArgs {
     cudaStream_t st;
     // bootstrap
     u64* out; const u64* in; long B; const double2* bskF; const u64* luts; const int* lut_idx; long long* prof;
+    size_t bsk_ct_stride;      // > 0: one GGSW list per ciphertext (k_pbs<P, true>)
+    // batched CMUX
+    const u64* cm_pool; const int* cm_i0; const int* cm_i1; const int* cm_gi;
     // bsk conversion
     double2* outF; const u64* bsk; long npoly;
     // polymul
@@ -998,8 +1106,16 @@ struct PbsPlanOps {
         return per_sm * sms;
     }
     static int pbs(const PbsLaunchArgs& a) {
-        return launch_clustered(k_pbs<P>, P::C, P::NT, P::TM_CTA, smem_pbs(a.g), a.B, a.st, a.out, a.in, a.B, a.bskF, a.luts,
-                                a.lut_idx, a.g, a.twT, a.tw_mid, a.prof);
+        if (a.bsk_ct_stride)
+            return launch_clustered(k_pbs<P, true>, P::C, P::NT, P::TM_CTA, smem_pbs(a.g), a.B, a.st, a.out, a.in, a.B,
+                                    a.bskF, a.luts, a.lut_idx, a.g, a.twT, a.tw_mid, a.prof, a.bsk_ct_stride);
+        return launch_clustered(k_pbs<P, false>, P::C, P::NT, P::TM_CTA, smem_pbs(a.g), a.B, a.st, a.out, a.in, a.B, a.bskF,
+                                a.luts, a.lut_idx, a.g, a.twT, a.tw_mid, a.prof, (size_t)0);
+    }
+    static int cmux(const PbsLaunchArgs& a) {
+        const size_t smem = (size_t)a.g.J * P::BUF * 16 + (size_t)P::TW_SMEM * 16;
+        return launch_clustered(k_cmux<P>, P::C, P::NT, P::TM_CTA, smem, a.B, a.st, a.out, a.cm_pool, a.cm_i0, a.cm_i1,
+                                a.bskF, a.cm_gi, a.B, a.g, a.twT, a.tw_mid);
     }
     static int bsk(const PbsLaunchArgs& a) {
         const size_t smem = (size_t)P::BUF * 16 + (size_t)P::TW_SMEM * 16;
@@ -1019,8 +1135,9 @@ struct PbsPlanEntry {
     int (*pbs)(const PbsLaunchArgs&);
     int (*bsk)(const PbsLaunchArgs&);
     int (*polymul)(const PbsLaunchArgs&);
+    int (*cmux)(const PbsLaunchArgs&);
 };
 
 #define PBS_PLAN_ENTRY(...) \
     PbsPlanEntry { PbsPlanOps<__VA_ARGS__>::meta(), &PbsPlanOps<__VA_ARGS__>::capacity, &PbsPlanOps<__VA_ARGS__>::pbs, &PbsPlanOps<__VA_ARGS__>::bsk, \
-                   &PbsPlanOps<__VA_ARGS__>::polymul }
+                   &PbsPlanOps<__VA_ARGS__>::polymul, &PbsPlanOps<__VA_ARGS__>::cmux }

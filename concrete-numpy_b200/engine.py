@@ -34,6 +34,20 @@ class CryptoParams:
     ks_base_log: int
     lwe_std: float         # noise std of the small key (relative to q)
     glwe_std: float        # noise std of the big key
+    # wide integers (p > 8, wide.py): CRT moduli of the residues every value is split into, circuit-bootstrap and
+    # packing-keyswitch decompositions; empty / zero for the native one-ciphertext-per-value encoding
+    moduli: tuple = ()
+    cbs_level: int = 0
+    cbs_base_log: int = 0
+    pf_level: int = 0
+    pf_base_log: int = 0
+
+    def __post_init__(self):
+        object.__setattr__(self, "moduli", tuple(int(m) for m in self.moduli))
+
+    @property
+    def wide(self) -> bool:
+        return len(self.moduli) > 0
 
     @property
     def big_dim(self) -> int:
@@ -89,6 +103,11 @@ class KeySet:
                       self.seed, scratch.data_ptr(), st)
             self.bsk_std = bsk_std if keep_std_bsk else None
             self.bsk_f = bsk_std_to_fourier(bsk_std, p)
+            self.pfksk = None
+            if p.wide:
+                from . import wide
+
+                self.pfksk = wide.keygen_packing_key(p, self.sk_big, self.seed)
             torch.cuda.current_stream().synchronize()
 
     # sizes reported through CompilationFeedback (reference server.py:296-350)
@@ -125,10 +144,18 @@ class EvalKeys:
     sequential circuit) is run on the largest cluster size that still bootstraps the whole batch at once;
     the Fourier BSK is permuted into that variant's layout on first use and cached."""
 
-    def __init__(self, params: CryptoParams, bsk_f: torch.Tensor, ksk: torch.Tensor):
+    def __init__(self, params: CryptoParams, bsk_f: torch.Tensor, ksk: torch.Tensor,
+                 pfksk: Optional[torch.Tensor] = None):
         self.params = params
         self.bsk_f = bsk_f
         self.ksk = ksk
+        self.pfksk = pfksk
+        self.packing = None         # packing keyswitch of the wide-integer lookup (wide.py)
+        self.wide_cache = {}        # small device constants of that lookup
+        if pfksk is not None:
+            from . import wide
+
+            self.packing = wide.PackingKey(params, pfksk)
         self._variants = {0: bsk_f}
         lib = _lib.load()
         n = lib.fhe_pbs_num_variants(params.N, params.k, params.pbs_level)
@@ -176,7 +203,7 @@ class EvalKeys:
 
     @staticmethod
     def of(keyset: KeySet) -> "EvalKeys":
-        return EvalKeys(keyset.params, keyset.bsk_f, keyset.ksk)
+        return EvalKeys(keyset.params, keyset.bsk_f, keyset.ksk, keyset.pfksk)
 
 
 # ------------------------------------------------------------------ client side ----
@@ -190,6 +217,19 @@ def encrypt(keyset: KeySet, messages: np.ndarray, first_index: int = 0, seed: Op
     ct = torch.empty((m.size, p.ct_words), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _lib.call("fhe_encrypt_lwe_batch", ct.data_ptr(), pt.data_ptr(), m.size, keyset.sk_big.data_ptr(),
+                  p.big_dim, p.glwe_std, keyset.seed if seed is None else int(seed), int(first_index), _stream())
+    return ct
+
+
+def encrypt_plaintexts(keyset: KeySet, plaintexts: np.ndarray, first_index: int = 0, seed: Optional[int] = None) -> torch.Tensor:
+    """LWE-encrypt already encoded u64 plaintexts under the big key (CRT residues of the wide path)."""
+    p = keyset.params
+    dev = keyset.device
+    pt_np = np.ascontiguousarray(np.asarray(plaintexts).reshape(-1).astype(np.uint64))
+    pt = from_np_u64(pt_np, dev)
+    ct = torch.empty((pt_np.size, p.ct_words), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("fhe_encrypt_lwe_batch", ct.data_ptr(), pt.data_ptr(), pt_np.size, keyset.sk_big.data_ptr(),
                   p.big_dim, p.glwe_std, keyset.seed if seed is None else int(seed), int(first_index), _stream())
     return ct
 

@@ -101,6 +101,23 @@ int fhe_pbs_batch_variant(uint64_t* out, const uint64_t* in, long B, const void*
                           const uint64_t* luts, const int* lut_idx, int n, int k, int N, int level,
                           int base_log, int variant, void* stream);
 
+/* ---- wide integers (9..16 bits): building blocks of the CRT / without-padding lookup -----------------
+ * The reference announces this path through the `crt` list of its client parameters
+ * (concrete/numpy/compilation/client.py:213-235) and allows table lookups up to 16 bits
+ * (concrete/numpy/mlir/utils.py:16); the arithmetic lives in the absent wheel.  Host composition:
+ * concrete-numpy_b200/wide.py (bit extraction = keyswitch + sign bootstraps, circuit bootstrapping = bootstraps +
+ * packing keyswitch = fhe_keyswitch_batch[_tc] with (k+1)^2 N columns, Fourier conversion = fhe_bsk_to_fourier).
+ *
+ * fhe_cmux_batch: out[b] = pool[i0[b]] + GGSW[gi[b]] (x) (pool[i1[b]] - pool[i0[b]]) on GLWE ciphertexts of
+ * (k+1)N words (CMUX tree of vertical packing).
+ * fhe_blind_rotate_batch: the bootstrap's blind rotation + sample extraction with one list of n GGSWs per
+ * ciphertext (ct_stride double2 elements apart) instead of a bootstrap key. */
+int fhe_cmux_batch(uint64_t* out, const uint64_t* pool, const int* i0, const int* i1, const void* ggsw_f,
+                   const int* gi, long B, int k, int N, int level, int base_log, void* stream);
+int fhe_blind_rotate_batch(uint64_t* out, const uint64_t* in, long B, const void* ggsw_f, long ct_stride,
+                           const uint64_t* luts, const int* lut_idx, int n, int k, int N, int level,
+                           int base_log, void* stream);
+
 /* development aid: k_pbs accumulates per-phase clock64() deltas of CTA b < 16 into dev_buf[16*b .. 16*b+15]
  * (NULL switches it off); not part of the reference-facing surface */
 int fhe_pbs_set_profile(long long* dev_buf);

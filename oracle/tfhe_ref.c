@@ -236,7 +236,9 @@ void ref_keygen_bsk(u64 *bsk, const u64 *sk_small, int n, const u64 *sk_glwe, in
         int i = (int)(R / ((long)(k + 1) * level));
         u64 *row = bsk + (size_t)R * row_words;
         glwe_encrypt_zero(row, sk_glwe, k, N, std, seed, (u64)R);
-        if (sk_small[i]) row[(size_t)r * N] += 1ULL << (64 - (lv + 1) * base_log);
+        /* key entries are 0/1 for an LWE key; the extended key of the packing keyswitch (wide-integer
+         * path, ref_keygen_bsk is reused for it) also holds -1 for the body slot */
+        row[(size_t)r * N] += sk_small[i] * (1ULL << (64 - (lv + 1) * base_log));
     }
 }
 
@@ -506,8 +508,12 @@ static void cmux_rotate(const fft_plan *p, u64 *acc, int a, const cplx *ggsw_f, 
 }
 
 /* luts: [T][(k+1)*N] GLWE accumulators (mask polys normally zero); lut_idx[e] in [0,T) or NULL */
-void ref_pbs_batch(u64 *out, const u64 *in, long B, const double *bsk_f, const u64 *luts,
-                   const int32_t *lut_idx, int n, int k, int N, int level, int base_log) {
+/* bsk_ct_stride: 0 for a bootstrap (one key for the batch); for the blind rotation of the
+ * wide-integer lookup every ciphertext brings its own list of n Fourier GGSWs (cplx elements
+ * between the lists of consecutive ciphertexts). */
+void ref_pbs_batch_ex(u64 *out, const u64 *in, long B, const double *bsk_f, const u64 *luts,
+                      const int32_t *lut_idx, int n, int k, int N, int level, int base_log,
+                      long bsk_ct_stride) {
     const fft_plan *p = get_plan(N);
     int log2N = 0; while ((1 << log2N) < N) log2N++;
     const int M = N / 2;
@@ -529,8 +535,8 @@ void ref_pbs_batch(u64 *out, const u64 *in, long B, const double *bsk_f, const u
             for (int i = 0; i < n; i++) {
                 int at = modswitch(ct[i], log2N);
                 if (at == 0) continue;
-                cmux_rotate(p, acc, at, (const cplx *)bsk_f + (size_t)i * ggsw_c, k, N, level,
-                            base_log, tmp, dig, fin, fout);
+                cmux_rotate(p, acc, at, (const cplx *)bsk_f + (size_t)e * bsk_ct_stride + (size_t)i * ggsw_c,
+                            k, N, level, base_log, tmp, dig, fin, fout);
             }
             /* sample extract coefficient 0 */
             u64 *o = out + (size_t)e * ((size_t)k * N + 1);
@@ -542,6 +548,61 @@ void ref_pbs_batch(u64 *out, const u64 *in, long B, const double *bsk_f, const u
             o[(size_t)k * N] = acc[(size_t)k * N];
         }
         free(acc); free(tmp); free(dig); free(fin); free(fout);
+    }
+}
+
+void ref_pbs_batch(u64 *out, const u64 *in, long B, const double *bsk_f, const u64 *luts,
+                   const int32_t *lut_idx, int n, int k, int N, int level, int base_log) {
+    ref_pbs_batch_ex(out, in, B, bsk_f, luts, lut_idx, n, k, N, level, base_log, 0);
+}
+
+/* Batched CMUX on GLWE ciphertexts (selection tree of the wide-integer lookup, "vertical packing",
+ * Bergerat et al., "Parameter Optimization & Larger Precision for (T)FHE", 2022):
+ *   out[b] = pool[i0[b]] + ggsw[gi[b]] (x) (pool[i1[b]] - pool[i0[b]])
+ * pool: [P][(k+1)N] GLWE ciphertexts (plaintext polynomials are trivial GLWEs: zero mask);
+ * ggsw_f: [G][level][k+1][k+1][M] as produced by ref_bsk_to_fourier. */
+void ref_cmux_batch(u64 *out, const u64 *pool, const int32_t *i0, const int32_t *i1,
+                    const double *ggsw_f, const int32_t *gi, long B, int k, int N, int level,
+                    int base_log) {
+    const fft_plan *p = get_plan(N);
+    const int M = N / 2;
+    const size_t glwe = (size_t)(k + 1) * N;
+    const size_t ggsw_c = (size_t)level * (k + 1) * (k + 1) * M;
+#pragma omp parallel
+    {
+        u64 *diff = (u64 *)malloc(sizeof(u64) * glwe);
+        double *dig = (double *)malloc(sizeof(double) * (size_t)level * N);
+        cplx *fin = (cplx *)malloc(sizeof(cplx) * M);
+        cplx *fout = (cplx *)malloc(sizeof(cplx) * (size_t)(k + 1) * M);
+        i64 digits[64];
+#pragma omp for schedule(dynamic, 1)
+        for (long b = 0; b < B; b++) {
+            const u64 *d0 = pool + (size_t)i0[b] * glwe, *d1 = pool + (size_t)i1[b] * glwe;
+            const cplx *g = (const cplx *)ggsw_f + (size_t)gi[b] * ggsw_c;
+            u64 *o = out + (size_t)b * glwe;
+            for (size_t t = 0; t < glwe; t++) { diff[t] = d1[t] - d0[t]; o[t] = d0[t]; }
+            memset(fout, 0, sizeof(cplx) * (size_t)(k + 1) * M);
+            for (int c = 0; c <= k; c++) {
+                for (int t = 0; t < N; t++) {
+                    signed_decompose(diff[(size_t)c * N + t], base_log, level, digits);
+                    for (int lv = 0; lv < level; lv++) dig[(size_t)lv * N + t] = (double)digits[lv];
+                }
+                for (int lv = 0; lv < level; lv++) {
+                    negacyclic_fwd(p, dig + (size_t)lv * N, fin);
+                    const cplx *row = g + ((size_t)lv * (k + 1) + c) * (k + 1) * M;
+                    for (int oo = 0; oo <= k; oo++) {
+                        const cplx *gg = row + (size_t)oo * M;
+                        cplx *dst = fout + (size_t)oo * M;
+                        for (int t = 0; t < M; t++) {
+                            dst[t].re += fin[t].re * gg[t].re - fin[t].im * gg[t].im;
+                            dst[t].im += fin[t].re * gg[t].im + fin[t].im * gg[t].re;
+                        }
+                    }
+                }
+            }
+            for (int oo = 0; oo <= k; oo++) negacyclic_inv_add(p, fout + (size_t)oo * M, o + (size_t)oo * N);
+        }
+        free(diff); free(dig); free(fin); free(fout);
     }
 }
 
