@@ -155,7 +155,15 @@ class Client:
         cleaned = []
         for index, out in enumerate(outputs):
             n = specs[index]["shape"]["width"]
-            if self.specs.output_signs[index]:                    # client.py:237-250
+            crt = ((specs[index].get("encryption") or {}).get("encoding") or {}).get("crt") or []
+            if self.specs.output_signs[index] and crt:            # client.py:217-235: values live mod prod(crt)
+                M = int(np.prod([int(m) for m in crt], dtype=object))
+                if isinstance(out, int):
+                    cleaned.append(out if out < M // 2 else out - M)
+                else:
+                    o = out.astype(np.int64)
+                    cleaned.append(np.where(o < M // 2, o, o - M).astype(np.int64))
+            elif self.specs.output_signs[index]:                  # client.py:237-250
                 if isinstance(out, int):
                     out %= 1 << n
                     cleaned.append(out if out < (1 << (n - 1)) else out - (1 << n))

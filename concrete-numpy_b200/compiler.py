@@ -125,7 +125,7 @@ def _gate(t, crypto: CryptoParams) -> dict:
     enc = None
     if t.encrypted:
         enc = {"secretKeyID": "big", "variance": crypto.glwe_std ** 2,
-               "encoding": {"precision": t.width, "crt": []}}
+               "encoding": {"precision": t.width, "crt": [int(m) for m in crypto.moduli]}}
     return {"shape": {"width": t.width, "dimensions": list(t.dims), "size": t.size, "sign": False},
             "encryption": enc}
 
@@ -134,11 +134,18 @@ class CompilationFeedback:
     """Attributes read by Server (server.py:296-350)."""
 
     def __init__(self, info: ProgramInfo, crypto: CryptoParams, program: Program, p_error: float):
-        L = crypto.ct_words
-        self.complexity = float(P.complexity(crypto, info.n_pbs))
+        L = crypto.ct_words * max(len(crypto.moduli), 1)          # words per encrypted element (all residues)
         self.total_secret_keys_size = int(8 * (crypto.n + crypto.big_dim))
         self.total_bootstrap_keys_size = int(8 * crypto.n * crypto.pbs_level * (crypto.k + 1) ** 2 * crypto.N)
         self.total_keyswitch_keys_size = int(8 * crypto.big_dim * crypto.ks_level * (crypto.n + 1))
+        if crypto.wide:
+            from . import wide
+
+            self.complexity = float(info.n_pbs * P.wide_lookup_flops(crypto))
+            self.total_keyswitch_keys_size += int(8 * (crypto.big_dim + wide.PF_PAD) * crypto.pf_level
+                                                  * (crypto.k + 1) ** 2 * crypto.N)
+        else:
+            self.complexity = float(P.complexity(crypto, info.n_pbs))
         self.total_inputs_size = int(sum(8 * L * t.size if t.encrypted else 8 * t.size for _, t in program.args))
         self.total_output_size = int(sum(8 * L * t.size if t.encrypted else 8 * t.size for t in program.result_types))
         self.p_error = float(p_error)
@@ -215,10 +222,15 @@ class LibraryLambda(ServerLambda):
 def _compile(mlir: str, options: CompilationOptions, cls):
     program = parse_module(mlir)
     info = analyze(program)
+    wide_mode = info.precision > 8          # beyond the native bootstrap: CRT residues + without-padding lookup (wide.py)
     if options.parameters_override is not None:
         crypto = options.parameters_override
         if crypto.p != info.precision:
             raise RuntimeError(f"pinned parameters carry {crypto.p} bits, circuit needs {info.precision}")
+        if crypto.wide:
+            info = analyze(program, crypto.moduli)
+        elif wide_mode:
+            raise RuntimeError(f"{info.precision}-bit circuits need CRT parameters (moduli)")
     else:
         n = max(info.n_pbs, 1)
         per_tlu = 1.0 - (1.0 - options.global_p_error) ** (1.0 / n) if options.global_p_error < 1.0 else 1.0
@@ -230,10 +242,19 @@ def _compile(mlir: str, options: CompilationOptions, cls):
         norm2_q = float(2 ** math.ceil(math.log2(max(info.norm2, 1.0))))
         target_q = float(10.0 ** math.floor(math.log10(target) + 1e-9))
         try:
-            crypto = P.select_parameters(info.precision, norm2_q, target_q)
+            if wide_mode:
+                from . import wide
+
+                if info.precision > 16:
+                    raise ValueError(f"{info.precision}-bit integers exceed the 16-bit limit of table lookups")
+                info = analyze(program, wide.crt_moduli(info.precision))
+                norm2_q = float(2 ** math.ceil(math.log2(max(info.norm2, 1.0))))
+                crypto = P.select_wide_parameters(info.precision, norm2_q, target_q)
+            else:
+                crypto = P.select_parameters(info.precision, norm2_q, target_q)
         except ValueError as error:
             raise RuntimeError(f"Unfeasible parameter search: {error}") from error
-    p_err = P.estimate_p_error(crypto, info.norm2)
+    p_err = P.estimate_wide_p_error(crypto, info.norm2) if crypto.wide else P.estimate_p_error(crypto, info.norm2)
     if options.display_optimizer_choice:
         print(f"--- Circuit\n  {info.precision} bits integers\n  {info.norm2:g} manp (squared 2-norm)\n"
               f"  {info.n_pbs} table lookups, depth {info.tlu_depth}\n--- Optimizer choice\n  {crypto}\n"
@@ -332,27 +353,33 @@ class KeySetCache:
 class EvaluationKeys:
     """BSK (Fourier) + KSK, device resident on the server; bytes on the wire."""
 
-    def __init__(self, crypto: CryptoParams, bsk_f: torch.Tensor, ksk: torch.Tensor):
+    def __init__(self, crypto: CryptoParams, bsk_f: torch.Tensor, ksk: torch.Tensor,
+                 pfksk: Optional[torch.Tensor] = None):
         self.crypto = crypto
         self.bsk_f = bsk_f
         self.ksk = ksk
+        self.pfksk = pfksk          # packing keyswitch key of the wide-integer lookup (None for native widths)
         self._per_device: Dict[str, E.EvalKeys] = {}
 
     def on(self, device) -> E.EvalKeys:
         key = str(torch.device(device))
         if key not in self._per_device:
-            self._per_device[key] = E.EvalKeys(self.crypto, self.bsk_f.to(device), self.ksk.to(device))
+            self._per_device[key] = E.EvalKeys(self.crypto, self.bsk_f.to(device), self.ksk.to(device),
+                                               None if self.pfksk is None else self.pfksk.to(device))
         return self._per_device[key]
 
     def serialize(self) -> bytes:
         header = json.dumps({"crypto": self.crypto.to_dict(), "bsk_shape": list(self.bsk_f.shape),
-                             "ksk_shape": list(self.ksk.shape)}).encode()
+                             "ksk_shape": list(self.ksk.shape),
+                             "pfksk_shape": None if self.pfksk is None else list(self.pfksk.shape)}).encode()
         buf = io.BytesIO()
         buf.write(_MAGIC + b"EVK")
         buf.write(struct.pack("<I", len(header)))
         buf.write(header)
         buf.write(self.bsk_f.detach().cpu().numpy().tobytes())
         buf.write(self.ksk.detach().cpu().numpy().tobytes())
+        if self.pfksk is not None:
+            buf.write(self.pfksk.detach().cpu().numpy().tobytes())
         return buf.getvalue()
 
     @staticmethod
@@ -369,8 +396,13 @@ class EvaluationKeys:
         bsk = np.frombuffer(data, dtype=np.float64, count=nb // 8, offset=off).reshape(h["bsk_shape"])
         off += nb
         ksk = np.frombuffer(data, dtype=np.int64, count=int(np.prod(h["ksk_shape"])), offset=off).reshape(h["ksk_shape"])
+        off += ksk.size * 8
         dev = default_device() if device is None else device
-        return EvaluationKeys(crypto, torch.from_numpy(bsk.copy()).to(dev), torch.from_numpy(ksk.copy()).to(dev))
+        pfksk = None
+        if h.get("pfksk_shape"):
+            pf = np.frombuffer(data, dtype=np.int64, count=int(np.prod(h["pfksk_shape"])), offset=off).reshape(h["pfksk_shape"])
+            pfksk = torch.from_numpy(pf.copy()).to(dev)
+        return EvaluationKeys(crypto, torch.from_numpy(bsk.copy()).to(dev), torch.from_numpy(ksk.copy()).to(dev), pfksk)
 
 
 _KEYSET_MEMO: Dict[tuple, E.KeySet] = {}
@@ -382,7 +414,7 @@ class KeySet:
         self._enc_counter = 0
 
     def get_evaluation_keys(self) -> EvaluationKeys:
-        return EvaluationKeys(self.keys.params, self.keys.bsk_f, self.keys.ksk)
+        return EvaluationKeys(self.keys.params, self.keys.bsk_f, self.keys.ksk, self.keys.pfksk)
 
 
 # ---------------------------------------------------------- arguments / results ---
@@ -494,10 +526,18 @@ class ClientSupport:
             if m.size and int(m.max()) >= (1 << width):
                 raise RuntimeError(f"argument value does not fit {width} bits")
             # fresh mask/noise streams for every call: object ids never repeat under one key
-            ct = E.encrypt(keyset.keys, m, first_index=keyset._enc_counter,
-                           seed=keyset.keys.seed ^ 0x5EEDC0DEC0FFEE)
-            keyset._enc_counter += int(m.size)
-            _ = crypto
+            if crypto.wide:
+                # one ciphertext per CRT residue, rows residue-major: [residue][element]
+                from . import wide
+
+                pts = np.concatenate([wide.encode_residue(m.astype(np.int64), mod) for mod in crypto.moduli])
+                ct = E.encrypt_plaintexts(keyset.keys, pts, first_index=keyset._enc_counter,
+                                          seed=keyset.keys.seed ^ 0x5EEDC0DEC0FFEE)
+                keyset._enc_counter += int(pts.size)
+            else:
+                ct = E.encrypt(keyset.keys, m, first_index=keyset._enc_counter,
+                               seed=keyset.keys.seed ^ 0x5EEDC0DEC0FFEE)
+                keyset._enc_counter += int(m.size)
             values.append(Ct(ct, shape))
         return PublicArguments(values)
 
@@ -507,7 +547,16 @@ class ClientSupport:
         outs = []
         for v, spec in zip(public_result.values, specs):
             shape = tuple(spec["shape"]["dimensions"])
-            if isinstance(v, Ct):
+            crypto = keyset.keys.params
+            if isinstance(v, Ct) and crypto.wide:
+                # CRT: decode every residue, recombine; the value lives mod prod(moduli) (client.py:217-235)
+                from . import wide
+
+                _, phase = E.decrypt(keyset.keys, v.data.to(keyset.keys.device), return_phase=True)
+                per = phase.reshape(len(crypto.moduli), -1)
+                m = wide.crt_combine([wide.decode_residue(per[i], mod) for i, mod in enumerate(crypto.moduli)],
+                                     crypto.moduli).astype(np.uint64)
+            elif isinstance(v, Ct):
                 m = E.decrypt(keyset.keys, v.data.to(keyset.keys.device))
                 width = spec["shape"]["width"]
                 m = m & np.uint64((1 << (width + 1)) - 1)

@@ -45,8 +45,16 @@ class ProgramInfo:
 TLU_OPS = {"FHE.apply_lookup_table", "FHELinalg.apply_lookup_table", "FHELinalg.apply_mapped_lookup_table"}
 
 
-def analyze(program: Program) -> ProgramInfo:
-    """Static pass: precision, PBS count / depth and the noise growth of the linear parts."""
+def _centered(c: np.ndarray, m: int) -> np.ndarray:
+    """Representative of c mod m in [-m/2, m/2): what a residue ciphertext is actually multiplied by."""
+    c = np.asarray(c, dtype=np.int64)
+    return np.mod(c + m // 2, m) - m // 2
+
+
+def analyze(program: Program, moduli: Tuple[int, ...] = ()) -> ProgramInfo:
+    """Static pass: precision, PBS count / depth and the noise growth of the linear parts.  With CRT `moduli`
+    (wide integers) every clear weight acts modulo each modulus, so the norms are taken over the centred residues
+    of the weights (worst modulus)."""
     widths = {t.width for _, t in program.args if t.encrypted}
     for op in program.ops:
         if op.result_type is not None and op.result_type.encrypted:
@@ -65,11 +73,18 @@ def analyze(program: Program) -> ProgramInfo:
             clear_bound[name] = float(2 ** t.width)
     n_pbs, worst = 0, 1.0
 
+    def reductions(c: np.ndarray) -> List[np.ndarray]:
+        return [_centered(c, m) for m in moduli] if moduli else [np.asarray(c)]
+
+    def stat(c: np.ndarray, fn) -> float:
+        return max(float(fn(r.astype(np.float64))) for r in reductions(c))
+
     def cmax(name: str) -> float:
         if name in const:
             c = const[name]
-            return float(np.max(np.abs(c.astype(np.float64)))) if c.size else 0.0
-        return clear_bound.get(name, 1.0)
+            return stat(c, lambda r: np.max(np.abs(r))) if c.size else 0.0
+        bound = clear_bound.get(name, 1.0)
+        return min(bound, max(moduli) / 2.0) if moduli else bound
 
     for op in program.ops:
         r, o = op.result, op.operands
@@ -96,15 +111,14 @@ def analyze(program: Program) -> ProgramInfo:
             v = 0.0
         elif base == "dot_eint_int":
             c = const.get(o[1])
-            v = nu[o[0]] * (float(np.sum(c.astype(np.float64) ** 2)) if c is not None
+            v = nu[o[0]] * (stat(c, lambda r: np.sum(r ** 2)) if c is not None
                             else cmax(o[1]) ** 2 * op.operand_types[0].size)
         elif base in ("matmul_eint_int", "matmul_int_eint"):
             ct_i, cl_i = (0, 1) if base == "matmul_eint_int" else (1, 0)
             c = const.get(o[cl_i])
             axis = -2 if base == "matmul_eint_int" else -1
             if c is not None:
-                c2 = c.astype(np.float64) ** 2
-                s = float(np.max(c2.sum(axis=axis if c.ndim > 1 else 0))) if c.size else 0.0
+                s = stat(c, lambda r: np.max((r ** 2).sum(axis=axis if r.ndim > 1 else 0))) if c.size else 0.0
             else:
                 kdim = op.operand_types[cl_i].dims[axis if len(op.operand_types[cl_i].dims) > 1 else 0]
                 s = cmax(o[cl_i]) ** 2 * kdim
@@ -112,7 +126,7 @@ def analyze(program: Program) -> ProgramInfo:
         elif base == "conv2d":
             c = const.get(o[1])
             if c is not None:
-                s = float(np.max((c.astype(np.float64) ** 2).reshape(c.shape[0], -1).sum(axis=1)))
+                s = stat(c, lambda r: np.max((r ** 2).reshape(r.shape[0], -1).sum(axis=1)))
             else:
                 wt = op.operand_types[1]
                 s = cmax(o[1]) ** 2 * (wt.size // wt.dims[0])
@@ -171,6 +185,11 @@ class Executor:
 
             self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.L = params.ct_words
+        # wide integers: every encrypted value is a list of CRT residues; the linear ops run once per residue
+        # ("lane", self._res) with that residue's plaintext encoding and weights reduced mod m, lookups see all lanes
+        self.moduli = tuple(params.moduli)
+        self.lanes = max(len(self.moduli), 1)
+        self._res = 0
         self._plans: Dict[int, dict] = {}          # per-op cached host plans + device uploads
         self._consts: Dict[str, np.ndarray] = {}
         for op in program.ops:
@@ -198,31 +217,49 @@ class Executor:
         return torch.from_numpy(a).to(self.device)
 
     def _plan(self, op: Op, build: Callable[[], dict]) -> dict:
-        key = id(op)
+        key = (id(op), self._res)
         if key not in self._plans:
             self._plans[key] = build()
         return self._plans[key]
 
     def _encode(self, c: np.ndarray) -> np.ndarray:
-        """clear ints -> plaintexts: (c mod 2^(p+1)) << (63 - p), as int64 bit patterns."""
+        """clear ints -> plaintexts: (c mod 2^(p+1)) << (63 - p), or the residue encoding of the current lane
+        (c mod m) * 2^64 / m; as int64 bit patterns."""
+        if self.moduli:
+            from . import wide
+
+            return wide.encode_residue(c, self.moduli[self._res]).view(np.int64)
         p = self.params.p
         v = (np.asarray(c, dtype=np.int64).astype(np.uint64) & np.uint64((1 << (p + 1)) - 1)) << np.uint64(63 - p)
         return v.view(np.int64)
 
+    def _weights(self, w: np.ndarray) -> np.ndarray:
+        """Clear multipliers as applied to the current lane (centred residues mod m keep the noise growth small)."""
+        w = np.asarray(w, dtype=np.int64)
+        return _centered(w, self.moduli[self._res]) if self.moduli else w
+
     # ---------------------------------------------------------------- run ---------
     def run(self, ev: EvalKeys, args: List) -> List:
         """args: one entry per function argument (Ct for encrypted, numpy array / int for clear)."""
-        env: Dict[str, object] = {}
+        R = self.lanes
+        envs: List[Dict[str, object]] = [{} for _ in range(R)]
         for (name, t), a in zip(self.program.args, args):
             if t.encrypted:
                 if not isinstance(a, Ct):
                     raise RuntimeError(f"argument {name} must be encrypted")
                 if tuple(a.shape) != t.dims:
                     raise RuntimeError(f"argument {name}: shape {a.shape} != {t.dims}")
-                env[name] = a
+                rows = a.data.shape[0] // R
+                if rows * R != a.data.shape[0] or rows != max(t.size, 1):
+                    raise RuntimeError(f"argument {name}: {a.data.shape[0]} ciphertexts for {t.size} elements x {R} residues")
+                for i in range(R):       # residue-major rows: [residue][element]; own buffers (rows are an odd
+                    # number of words long, a row slice would break the 16-byte alignment the kernels vectorise on)
+                    envs[i][name] = a if R == 1 else Ct(a.data[i * rows:(i + 1) * rows].clone(), a.shape)
             else:
-                env[name] = np.asarray(a, dtype=np.int64).reshape(t.dims)
-        env.update(self._consts)
+                for i in range(R):
+                    envs[i][name] = np.asarray(a, dtype=np.int64).reshape(t.dims)
+        for env in envs:
+            env.update(self._consts)
         self._ev = ev
         n_pbs = 0
         for op in self.program.ops:
@@ -232,11 +269,26 @@ class Executor:
             h = self.handlers.get(base)
             if h is None:
                 raise RuntimeError(f"operation {op.name} is not supported by the B200 backend")
-            env[op.result] = h(op, [env[x] for x in op.operands])
+            if self.moduli and base in ("apply_lookup_table", "apply_mapped_lookup_table"):
+                outs = self._tlu_wide(op, [[env[x] for x in op.operands] for env in envs])
+                for env, o in zip(envs, outs):
+                    env[op.result] = o
+            else:
+                for i, env in enumerate(envs):
+                    self._res = i
+                    env[op.result] = h(op, [env[x] for x in op.operands])
+                self._res = 0
             if base in ("apply_lookup_table", "apply_mapped_lookup_table"):
                 n_pbs += op.result_type.size
         self.last_stats = {"n_pbs": n_pbs}
-        return [env[r] for r in self.program.returns]
+        results = []
+        for r in self.program.returns:
+            vals = [env[r] for env in envs]
+            if R > 1 and isinstance(vals[0], Ct):
+                results.append(Ct(torch.cat([v.data for v in vals], dim=0), vals[0].shape))
+            else:
+                results.append(vals[0])
+        return results
 
     # ------------------------------------------------------------- elementwise ----
     def _binary_ct(self, op: Op, a: Ct, b: Ct, fn) -> Ct:
@@ -263,13 +315,13 @@ class Executor:
 
         if cname not in self._consts:
             return build()
-        key = ("clear", id(op))
+        key = ("clear", id(op), self._res)
         if key not in self._plans:
             self._plans[key] = build()
         return self._plans[key]
 
     def _ct_map(self, op: Op, a: Ct, shape):
-        key = ("ia", id(op))
+        key = ("ia", id(op), self._res)
         if key not in self._plans:
             self._plans[key] = self._dev(_row_map(a.shape, shape))
         return self._plans[key]
@@ -294,7 +346,7 @@ class Executor:
 
     def _mul_eint_int(self, op, v):      # ct * clear int (all words), node_converter.py:630-650
         shape = op.result_type.dims
-        c = self._clear_operand(op, v[1], shape, encode=False)
+        c = self._clear_operand(op, self._weights(v[1]), shape, encode=False)
         return Ct(E.lin_mul_clear(v[0].data, c, self.L, self._ct_map(op, v[0], shape)), shape)
 
     def _zero(self, op, v):              # trivial encryption of 0: all-zero LWE (node_converter.py:1232-1248)
@@ -327,6 +379,53 @@ class Executor:
             out = self._tlu_sharded(x.data, plan["luts"], plan["idx"])
         return Ct(out, op.result_type.dims)
 
+    def _tlu_wide(self, op, lanes_v):
+        """Lookup on CRT residues (wide.py): bit extraction + circuit bootstrapping once, vertical packing per output
+        residue.  lanes_v[i] = operand values of lane i (ciphertext residues differ, clear operands are shared)."""
+        from . import wide
+
+        p = self.params
+        v0 = lanes_v[0]
+        xs = [v[0] for v in lanes_v]
+        self._res = 0
+
+        def build():
+            tables = np.asarray(v0[1], dtype=np.int64)
+            if tables.ndim == 1:
+                tables = tables[None, :]
+            if tables.shape[1] != (1 << p.p):
+                raise RuntimeError(f"lookup table of {tables.shape[1]} entries on {p.p}-bit ciphertexts")
+            luts = wide.build_crt_luts(tables, self.moduli)
+            idx = None
+            if op.name.endswith("apply_mapped_lookup_table"):
+                m = np.broadcast_to(np.asarray(v0[2], dtype=np.int64), xs[0].shape).reshape(-1)
+                idx = self._dev(m.astype(np.int64))
+            return {"pool": wide.lut_pool(p, luts, self.device), "polys": max(luts.shape[2] // p.N, 1), "idx": idx}
+
+        plan = self._plan(op, build)
+        rows = [x.data for x in xs]
+        n = rows[0].shape[0]
+        if self.world == 1:
+            outs = wide.wide_table_lookup(self._ev, rows, plan["pool"], plan["polys"], plan["idx"])
+        else:
+            import torch.distributed as dist
+
+            per = (n + self.world - 1) // self.world
+            lo = min(self.rank * per, n)
+            hi = min(lo + per, n)
+            mine = [torch.zeros((per, self.L), dtype=torch.int64, device=self.device) for _ in rows]
+            if hi > lo:
+                sub = wide.wide_table_lookup(self._ev, [r[lo:hi].clone() for r in rows], plan["pool"], plan["polys"],
+                                             None if plan["idx"] is None else plan["idx"][lo:hi].contiguous())
+                for m_, s_ in zip(mine, sub):
+                    m_[: hi - lo] = s_
+            outs = []
+            for m_ in mine:
+                full = torch.empty((per * self.world, self.L), dtype=torch.int64, device=self.device)
+                dist.all_gather_into_tensor(full, m_, group=self.group)
+                outs.append(full[:n].contiguous())
+        return [Ct(o, op.result_type.dims) for o in outs]
+
     def _tlu_sharded(self, rows: torch.Tensor, luts, idx):
         """Rank r bootstraps rows [r*per, (r+1)*per) and all ranks gather the result."""
         import torch.distributed as dist
@@ -347,7 +446,7 @@ class Executor:
     def _gather(self, op: Op, x: Ct, build: Callable[[], Tuple[np.ndarray, np.ndarray, Optional[np.ndarray]]]) -> Ct:
         def mk():
             idx, w, bias = build()
-            return {"idx": self._dev(idx.astype(np.int32)), "w": self._dev(w.astype(np.int64)),
+            return {"idx": self._dev(idx.astype(np.int32)), "w": self._dev(self._weights(w).astype(np.int64)),
                     "bias": None if bias is None else self._dev(self._encode(bias))}
 
         clear_names = [n for n, t in zip(op.operands, op.operand_types) if not t.encrypted]
@@ -371,9 +470,9 @@ class Executor:
             Mr, K = x.shape
             wname = op.operands[1]
             if wname in self._consts:
-                Wd = self._plan(op, lambda: {"W": self._dev(W)})["W"]
+                Wd = self._plan(op, lambda: {"W": self._dev(self._weights(W))})["W"]
             else:
-                Wd = self._dev(W)
+                Wd = self._dev(self._weights(W))
             return Ct(E.matmul_ct_clear(x.data, Wd, Mr, K, W.shape[1], self.L), out_shape)
 
         def build():

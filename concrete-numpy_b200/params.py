@@ -182,6 +182,146 @@ def select_parameters(p: int, norm2: float = 1.0, p_error: float = 1e-9) -> Cryp
                         glwe_std=2.0 ** secure_log2_std(k * N))
 
 
+# ---------------------------------------------------------------- wide integers (CRT) ----
+
+def variance_packing_keyswitch(kN, level, base_log, glwe_var):
+    """Noise the packing keyswitch of circuit bootstrapping adds to a GGSW row (wide.py)."""
+    B2 = 4.0 ** base_log
+    return (kN + 1) * level * (B2 + 2.0) / 12.0 * glwe_var + (kN / 2.0) / (12.0 * 4.0 ** (base_log * level))
+
+
+def variance_cmux(k, N, level, base_log, ggsw_var):
+    """One external product of vertical packing with a circuit-bootstrapped GGSW of row variance ggsw_var."""
+    B2 = 4.0 ** base_log
+    ext = level * (k + 1) * N * (B2 + 2.0) / 12.0 * ggsw_var
+    rounding = (1.0 + k * N / 2.0) / (12.0 * 4.0 ** (base_log * level))
+    fft = level * (k + 1) * B2 * float(N) ** 2 * 2.0 ** (-2.577 + 22 - 128)
+    return ext + rounding + fft
+
+
+def wide_output_variance(params: CryptoParams) -> float:
+    """Variance of a residue ciphertext coming out of a wide lookup (depth = number of extracted bits)."""
+    from .wide import total_bits
+
+    g2 = params.glwe_std ** 2
+    v_pbs = variance_pbs_out(params.n, params.k, params.N, params.pbs_level, params.pbs_base_log, g2)
+    v_ggsw = v_pbs + variance_packing_keyswitch(params.big_dim, params.pf_level, params.pf_base_log, g2)
+    return total_bits(params.moduli) * variance_cmux(params.k, params.N, params.cbs_level, params.cbs_base_log, v_ggsw)
+
+
+def wide_sign_tests(params: CryptoParams, norm2: float):
+    """(margin, variance) of every sign test of bit extraction: residue m with b bits, bit t."""
+    from .wide import block_layout
+
+    g2 = params.glwe_std ** 2
+    v_pbs = variance_pbs_out(params.n, params.k, params.N, params.pbs_level, params.pbs_base_log, g2)
+    v_in = max(wide_output_variance(params), g2) * max(norm2, 1.0)
+    v_small = (variance_keyswitch(params.big_dim, params.ks_level, params.ks_base_log, params.lwe_std ** 2)
+               + variance_modswitch(params.n, params.N))
+    tests = []
+    for m in params.moduli:
+        b, _, _, cells = block_layout(int(m))
+        for t in range(b):
+            margin = cells / 2.0 if t == 0 else 0.25 * (1.0 - 2.0 ** -t)
+            tests.append((margin, 4.0 ** (b - 1 - t) * (v_in + t * v_pbs) + v_small))
+    return tests
+
+
+def estimate_wide_p_error(params: CryptoParams, norm2: float) -> float:
+    """Probability that one wide lookup takes a wrong sign decision (union bound over its extracted bits)."""
+    return min(1.0, sum(math.erfc(m / math.sqrt(2.0 * v)) for m, v in wide_sign_tests(params, norm2)))
+
+
+def wide_lookup_flops(params: CryptoParams) -> float:
+    """fp64-equivalent work of one wide lookup (all residues)."""
+    from .wide import PF_PAD, block_bits, total_bits
+
+    T = total_bits(params.moduli)
+    n_boot = sum(block_bits(int(m)) - 1 for m in params.moduli) + T * params.cbs_level
+    M = params.N / 2
+    ext = ((params.k + 1) * (params.cbs_level + 1) * 5 * M * math.log2(M) + 8 * (params.k + 1) ** 2 * params.cbs_level * M)
+    logN = params.N.bit_length() - 1
+    vp = len(params.moduli) * ((1 << max(T - logN, 0)) + min(T, logN)) * ext
+    packing = 0.1 * KS_MAC_COST * T * params.cbs_level * (params.big_dim + PF_PAD) * params.pf_level * (params.k + 1) ** 2 * params.N
+    return (n_boot * pbs_flops(params.n, params.k, params.N, params.pbs_level)
+            + T * KS_MAC_COST * ks_macs(params.big_dim, params.n, params.ks_level) + packing + vp)
+
+
+@lru_cache(maxsize=None)
+def select_wide_parameters(p: int, norm2: float = 1.0, p_error: float = 1e-9) -> CryptoParams:
+    """Cheapest parameter set for p-bit values (9..16) carried as CRT residues: every sign test of a lookup must
+    hold with probability 1 - p_error / (number of extracted bits)."""
+    from .wide import block_layout, crt_moduli, total_bits
+
+    if p < 9 or p > 16:
+        raise ValueError(f"wide (CRT) encoding covers 9..16 bits, not {p}")
+    moduli = crt_moduli(p)
+    T = total_bits(moduli)
+    z = _z_for_p_error(p_error / T)
+    lay = [block_layout(m) for m in moduli]
+    best = None
+    n_grid = np.arange(500, 1101, 12)
+    lwe_var_grid = 4.0 ** np.maximum(SECURITY_SLOPE * n_grid + SECURITY_BIAS, MIN_LOG2_STD)
+    ks_options = [(lv, b) for lv in range(1, 10) for b in range(1, 8) if lv * b <= 40]
+    for k, N in [(1, 2048), (1, 4096), (2, 1024), (3, 512)]:
+        kN = k * N
+        g2 = 4.0 ** secure_log2_std(kN)
+        v_ms = (1.0 / 12.0 + n_grid / 24.0) / (4.0 * N * N)
+        # packing keyswitch on the tensor cores (base <= 2^7): smallest level whose noise hides under the bootstrap's
+        for pbs_level in (1, 2, 3, 4):
+            if pbs_cluster_size(N, k, pbs_level) < 0:
+                continue
+            for pbs_base_log in range(4, 27):
+                if pbs_level * pbs_base_log > 52:
+                    break
+                v_pbs = variance_pbs_out(1, k, N, pbs_level, pbs_base_log, g2) * n_grid
+                pf = None
+                for pf_level in range(2, 9):
+                    v_pf = variance_packing_keyswitch(kN, pf_level, 7, g2)
+                    if v_pf <= 0.25 * float(v_pbs.min()) or pf_level == 8:
+                        pf = (pf_level, 7, v_pf)
+                        break
+                for cbs_level in (1, 2, 3, 4):
+                    if pbs_cluster_size(N, k, cbs_level) < 0:
+                        continue
+                    for cbs_base_log in range(2, 16):
+                        if cbs_level * cbs_base_log > 40:
+                            break
+                        v_out = T * variance_cmux(k, N, cbs_level, cbs_base_log, v_pbs + pf[2])
+                        v_in = np.maximum(v_out, g2) * max(norm2, 1.0)
+                        # what the keyswitch may add: the tightest sign test decides
+                        budget = np.full(n_grid.shape, np.inf)
+                        for b, _, _, cells in lay:
+                            for t in range(b):
+                                margin = cells / 2.0 if t == 0 else 0.25 * (1.0 - 2.0 ** -t)
+                                budget = np.minimum(budget, (margin / z) ** 2 - 4.0 ** (b - 1 - t) * (v_in + t * v_pbs) - v_ms)
+                        if not np.any(budget > 0):
+                            continue
+                        probe = CryptoParams(p=p, n=int(n_grid[0]), k=k, N=N, pbs_level=pbs_level, pbs_base_log=pbs_base_log,
+                                             ks_level=1, ks_base_log=1, lwe_std=1.0, glwe_std=1.0, moduli=moduli,
+                                             cbs_level=cbs_level, cbs_base_log=cbs_base_log, pf_level=pf[0], pf_base_log=pf[1])
+                        c0 = wide_lookup_flops(probe)
+                        c1 = wide_lookup_flops(CryptoParams(**{**probe.to_dict(), "n": int(n_grid[-1])}))
+                        base_cost = c0 + (c1 - c0) * (n_grid - n_grid[0]) / (n_grid[-1] - n_grid[0])
+                        for ks_level, ks_base_log in ks_options:
+                            B2 = 4.0 ** ks_base_log
+                            v_ks = kN * ks_level * (B2 + 2.0) / 12.0 * lwe_var_grid + kN / 24.0 / 4.0 ** (ks_base_log * ks_level)
+                            ok = v_ks <= budget
+                            if not np.any(ok):
+                                continue
+                            cost = np.where(ok, base_cost + T * KS_MAC_COST * kN * (ks_level - 1) * (n_grid + 1), np.inf)
+                            j = int(np.argmin(cost))
+                            if best is None or cost[j] < best[0]:
+                                best = (float(cost[j]), int(n_grid[j]), k, N, pbs_level, pbs_base_log, ks_level, ks_base_log,
+                                        cbs_level, cbs_base_log, pf[0], pf[1])
+    if best is None:
+        raise ValueError(f"no wide parameter set reaches p_error={p_error:g} at {p} bits with 2-norm^2={norm2:g}")
+    _, n, k, N, pl, pb, kl, kb, cl, cb, fl, fb = best
+    return CryptoParams(p=p, n=n, k=k, N=N, pbs_level=pl, pbs_base_log=pb, ks_level=kl, ks_base_log=kb,
+                        lwe_std=2.0 ** secure_log2_std(n), glwe_std=2.0 ** secure_log2_std(k * N), moduli=moduli,
+                        cbs_level=cl, cbs_base_log=cb, pf_level=fl, pf_base_log=fb)
+
+
 def _z_for_p_error(p_error: float) -> float:
     """z such that erfc(z / sqrt(2)) == p_error (bisection; p_error in (0, 1))."""
     p_error = min(max(p_error, 1e-300), 0.999999)

@@ -366,7 +366,10 @@ def wide_table_lookup(ev, cts: Sequence[torch.Tensor], pool: torch.Tensor, polys
         n_ct = hi - lo
         blist: List[torch.Tensor] = []
         for ct, m in zip(cts, moduli):
-            blist += extract_bits(ev, ct[lo:hi].contiguous(), int(m))
+            part = ct[lo:hi]
+            if not part.is_contiguous() or part.data_ptr() % 16:       # the linear kernels vectorise on 16 bytes
+                part = part.clone()
+            blist += extract_bits(ev, part, int(m))
         stacked = torch.stack(blist, dim=1).reshape(n_ct * bits, p.n + 1)          # [e][t]
         ggsw_f = circuit_bootstrap(ev, stacked)
         tsel = torch.zeros(n_ct, dtype=torch.int64, device=stacked.device) if table_idx is None else table_idx[lo:hi].to(torch.int64)

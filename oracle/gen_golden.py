@@ -314,7 +314,37 @@ def known_answers():
     emit("ka_doc_table", lambda x: table[x], {"x": "encrypted"}, range(4), [0, 1, 2, 3])
 
 
-GROUPS = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "ops": ops, "ka": known_answers,
+def wide():
+    """Widths 9..16 (reference: MAXIMUM_TLU_BIT_WIDTH = 16, concrete/numpy/mlir/utils.py:16; the compiler switches
+    to a CRT encoding there, client.py:213-235).  Shapes follow tests/execution/test_add.py / test_mul.py /
+    test_matmul.py / test_others.py with larger value ranges."""
+    rng = np.random.default_rng(7)
+
+    def ins(lo, hi, shape, n=12):
+        return [rng.integers(lo, hi + 1, shape) for _ in range(n)] + [np.full(shape, lo, dtype=np.int64), np.full(shape, hi, dtype=np.int64)]
+
+    def pairs(a, b):
+        return list(zip(a, b))
+
+    emit("wide_square_div_10bit", lambda x: (x ** 2) // 3, {"x": "encrypted"}, ins(0, 31, (4,)),
+         [np.array([0, 31, 17, 5]), rng.integers(0, 32, (4,))])
+    emit("wide_linear_tlu_16bit", lambda x, y: (x * 3 + y) % 1000, {"x": "encrypted", "y": "encrypted"},
+         pairs(ins(0, 15000, (3,)), ins(0, 15000, (3,))),
+         [(np.array([15000, 0, 1234]), np.array([15000, 7, 4321])), (rng.integers(0, 15001, (3,)), rng.integers(0, 15001, (3,)))])
+    emit("wide_signed_abs_12bit", lambda x, y: np.abs(x - y) + 1, {"x": "encrypted", "y": "encrypted"},
+         pairs(ins(0, 2000, (3,)), ins(0, 2000, (3,))),
+         [(np.array([0, 2000, 1000]), np.array([2000, 0, 999])), (rng.integers(0, 2001, (3,)), rng.integers(0, 2001, (3,)))])
+    W = np.array([[100, -7], [3, 250], [-41, 9]], dtype=np.int64)
+    emit("wide_matmul_relu_14bit", lambda x: np.maximum(x @ W, 0) // 2, {"x": "encrypted"}, ins(0, 20, (2, 3)),
+         [np.array([[20, 20, 0], [0, 20, 20]]), rng.integers(0, 21, (2, 3))])
+    tables = cnp.LookupTable([cnp.LookupTable(((np.arange(512) * 5) % 301).tolist()), cnp.LookupTable((np.arange(512) // 2).tolist())])
+    emit("wide_multi_table_9bit", lambda x: tables[x], {"x": "encrypted"}, ins(0, 511, (2,)),
+         [np.array([511, 0]), rng.integers(0, 512, (2,))])
+    emit("wide_signed_output_11bit", lambda x: x * 7 - 3000, {"x": "encrypted"}, ins(0, 600, (3,)),
+         [np.array([0, 600, 429]), rng.integers(0, 601, (3,))])
+
+
+GROUPS = {"wide": wide, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "ops": ops, "ka": known_answers,
           "cfg5small": lambda: cfg5(8)}
 
 if __name__ == "__main__":

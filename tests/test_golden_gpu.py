@@ -20,6 +20,9 @@ FAST = [n for n in golden_names() if n.startswith(("ops_", "ka_", "cfg5_kvdb8", 
 HEAVY = [n for n in golden_names() if n.startswith(("cfg2", "cfg4", "cfg5_kvdb128"))]
 
 
+WIDE = [n for n in golden_names() if n.startswith("wide_")]      # 9..16-bit circuits: CRT residues + wide lookup
+
+
 def check(name):
     doc = load_golden(name)
     cfg = api.Configuration(jit=True, global_p_error=doc["global_p_error"])
@@ -37,6 +40,11 @@ def test_golden_encrypted_execution(cuda_device, name):
 
 @pytest.mark.parametrize("name", HEAVY)
 def test_golden_encrypted_execution_baseline_sizes(cuda_device, name):
+    check(name)
+
+
+@pytest.mark.parametrize("name", WIDE)
+def test_golden_wide_integers(cuda_device, name):
     check(name)
 
 
