@@ -135,11 +135,14 @@ extern "C" {
 
 #define LIN_ARGS_OK(E, L) ((E) >= 0 && (L) > 0)
 
+// the flat path moves 16-byte vectors: row slices of tensors with an odd row length may start 8 bytes off
+#define LIN_ALIGNED16(o, x, y) ((((uintptr_t)(o) | (uintptr_t)(x) | (uintptr_t)(y)) & 15) == 0)
+
 int fhe_lin_add(u64* out, const u64* a, const u64* b, const int* ia, const int* ib, long E, int L, void* stream) {
     if (!LIN_ARGS_OK(E, L)) FHE_FAIL(2, "lin_add: bad arguments");
     if (E == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!ia && !ib) {
+    if (!ia && !ib && LIN_ALIGNED16(out, a, b)) {
         long words = E * (long)L;
         int grid = (int)((words / 2 + 255) / 256 < 148L * 8 ? (words / 2 + 255) / 256 : 148L * 8);
         k_flat<0><<<grid < 1 ? 1 : grid, 256, 0, st>>>(out, a, b, words);
@@ -153,7 +156,7 @@ int fhe_lin_sub(u64* out, const u64* a, const u64* b, const int* ia, const int* 
     if (!LIN_ARGS_OK(E, L)) FHE_FAIL(2, "lin_sub: bad arguments");
     if (E == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!ia && !ib) {
+    if (!ia && !ib && LIN_ALIGNED16(out, a, b)) {
         long words = E * (long)L;
         int grid = (int)((words / 2 + 255) / 256 < 148L * 8 ? (words / 2 + 255) / 256 : 148L * 8);
         k_flat<1><<<grid < 1 ? 1 : grid, 256, 0, st>>>(out, a, b, words);
@@ -167,7 +170,7 @@ int fhe_lin_neg(u64* out, const u64* a, const int* ia, long E, int L, void* stre
     if (!LIN_ARGS_OK(E, L)) FHE_FAIL(2, "lin_neg: bad arguments");
     if (E == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!ia) {
+    if (!ia && LIN_ALIGNED16(out, a, a)) {
         long words = E * (long)L;
         int grid = (int)((words / 2 + 255) / 256 < 148L * 8 ? (words / 2 + 255) / 256 : 148L * 8);
         k_flat<2><<<grid < 1 ? 1 : grid, 256, 0, st>>>(out, a, nullptr, words);

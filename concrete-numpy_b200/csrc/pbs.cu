@@ -276,8 +276,9 @@ int fhe_blind_rotate_batch(u64* out, const u64* in, long B, const double2* ggsw_
 
 // out[b] = pool[i0[b]] + GGSW[gi[b]] (x) (pool[i1[b]] - pool[i0[b]]); pool [P][(k+1)N], out [B][(k+1)N],
 // ggsw_f: Fourier GGSWs in the variant-0 layout of (N, k, level) (fhe_bsk_to_fourier with n = their count)
+// plain != 0: every pool entry used is a plaintext polynomial (zero mask), only the bodies are transformed
 int fhe_cmux_batch(u64* out, const u64* pool, const int* i0, const int* i1, const double2* ggsw_f, const int* gi,
-                   long B, int k, int N, int level, int base_log, void* stream) {
+                   long B, int k, int N, int level, int base_log, int plain, void* stream) {
     if (B < 0) FHE_FAIL(2, "cmux_batch: negative batch");
     if (B == 0) return 0;
     PbsLaunchArgs a = {};
@@ -285,7 +286,7 @@ int fhe_cmux_batch(u64* out, const u64* pool, const int* i0, const int* i1, cons
     int rc = get_plan(1, k, N, level, base_log, 0, &e, &a);
     if (rc) return rc;
     a.st = (cudaStream_t)stream;
-    a.out = out; a.B = B; a.bskF = ggsw_f; a.cm_pool = pool; a.cm_i0 = i0; a.cm_i1 = i1; a.cm_gi = gi;
+    a.out = out; a.B = B; a.bskF = ggsw_f; a.cm_pool = pool; a.cm_i0 = i0; a.cm_i1 = i1; a.cm_gi = gi; a.cm_plain = plain;
     return e->cmux(a);
 }
 

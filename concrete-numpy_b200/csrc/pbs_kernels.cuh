@@ -912,17 +912,20 @@ k_polymul_test(u64* __restrict__ out, const i64* __restrict__ a_small, const u64
 
 // ---- batched CMUX on GLWE ciphertexts (selection tree of the wide-integer lookup) ------------------
 //   out[b] = pool[i0[b]] + GGSW[gi[b]] (x) (pool[i1[b]] - pool[i0[b]])
-// pool: [P][(k+1)N] u64 (plaintext polynomials are trivial GLWEs), GGSWs in the Fourier layout of this plan
-// (fhe_bsk_to_fourier with n = number of GGSWs).  One external product per work item: a few per lookup next
-// to the ~10^5 of its bootstraps, so this kernel favours reuse of the bootstrap's phases over tuning.
+// pool: [P][(k+1)N] u64, GGSWs in the Fourier layout of this plan (fhe_bsk_to_fourier with n = number of GGSWs).
+// `plain`: the inputs are plaintext polynomials (trivial GLWEs, zero masks -- the leaves of the tree): only the
+// body polynomial is decomposed and transformed.  The phases are the bootstrap's (stage 1 with fused
+// decomposition, mid passes, fused MAC, inverse passes, gather); the difference is read from global memory
+// instead of the rotated accumulator.
 template <class P>
 __global__ void __launch_bounds__(P::NT, P::MINB)
 k_cmux(u64* __restrict__ out, const u64* __restrict__ pool, const int* __restrict__ i0, const int* __restrict__ i1,
        const double2* __restrict__ ggswF, const int* __restrict__ gi, long B, const PbsGeom g,
-       const double2* __restrict__ twT, const double2* __restrict__ tw_mid) {
+       const double2* __restrict__ twT, const double2* __restrict__ tw_mid, int plain) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int C = P::C, R1 = P::R1, NT = P::NT, RF = P::RF, BUF = P::BUF, N = P::N, M = P::M, Q = P::Q;
     constexpr int NG = BUF / RF;
+    constexpr int MAXL = 4;                                  // get_plan() admits at most 4 levels
     const int k = g.k, level = g.level, J = g.J, base_log = g.base_log;
     double2* work = reinterpret_cast<double2*>(smem_raw);   // [J][BUF]
     int rank = 0;
@@ -930,24 +933,41 @@ k_cmux(u64* __restrict__ out, const u64* __restrict__ pool, const int* __restric
     const long cluster_id = blockIdx.x / C, nclusters = gridDim.x / C;
     const size_t glwe = (size_t)(k + 1) * N;
     const size_t ggsw_stride = (size_t)J * (k + 1) * C * BUF;
+    const int c_first = plain ? k : 0;                      // first GLWE component with a non-zero difference
+    const int j_first = c_first * level;
     const TwCtx tw = tw_setup<P>(work + (size_t)J * BUF, twT, tw_mid);
     csync<C>();
     for (long b = cluster_id; b < B; b += nclusters) {
         const u64* d0 = pool + (size_t)i0[b] * glwe;
         const u64* d1 = pool + (size_t)i1[b] * glwe;
         const double2* gg = ggswF + (size_t)gi[b] * ggsw_stride;
-        for (int c = 0; c <= k; c++)
-            for (int lv = 0; lv < level; lv++)
-                forward_poly<P>(work, c * level + lv, rank, g, tw, [&](int coef) {
-                    int dg[16];
-                    signed_decompose<16>(d1[(size_t)c * N + coef] - d0[(size_t)c * N + coef], base_log, level, dg);
-                    int d = 0;
+        // ---- decomposition of d1 - d0 fused into stage 1 (one item = the 2*R1 coefficients of a butterfly)
+#pragma unroll 1
+        for (int it = threadIdx.x; it < ((k + 1 - c_first) << P::LOGQ); it += NT) {
+            const int c = c_first + (it >> P::LOGQ), q = it & (Q - 1);
+            const int j2 = (rank << P::LOGQ) + q;
+            double2 T[R1];
+            load_T<P>(T, tw, j2);
+            int dg[2 * R1][MAXL];
 #pragma unroll
-                    for (int t = 0; t < 16; t++) d = (t == level - 1 - lv) ? dg[t] : d;
-                    return (double)d;
-                });
+            for (int hj = 0; hj < 2 * R1; hj++) {
+                const size_t coef = (size_t)c * N + (hj << P::LOGL1) + j2;
+                signed_decompose<MAXL>(d1[coef] - d0[coef], base_log, level, dg[hj]);
+            }
+#pragma unroll
+            for (int t = 0; t < MAXL; t++)
+                if (t < level) {                              // dg[.][t] is the digit of level index level-1-t
+                    double re[R1], im[R1];
+#pragma unroll
+                    for (int j1 = 0; j1 < R1; j1++) {
+                        re[j1] = (double)dg[j1][t];
+                        im[j1] = (double)dg[R1 + j1][t];
+                    }
+                    stage1_emit<P>(work + ((size_t)(c * level + level - 1 - t) << P::LOGBUF), j2, re, im, T, g);
+                }
+        }
         csync<C>();
-        mid_passes<P, false>(work, J, tw);
+        mid_passes<P, false>(work + ((size_t)j_first << P::LOGBUF), J - j_first, tw);
 #pragma unroll 1
         for (int w = threadIdx.x; w < NG; w += NT) {
             double2 r[P::KMAX + 1][RF];
@@ -958,19 +978,26 @@ k_cmux(u64* __restrict__ out, const u64* __restrict__ pool, const int* __restric
             const double2* gp = gg + ((size_t)rank << P::LOGBUF) + w;
             const size_t o_stride = (size_t)P::C << P::LOGBUF;
 #pragma unroll 1
-            for (int j = 0; j < J; j++) {
+            for (int j = j_first; j < J; j++) {
                 double2 x[RF];
                 const double2* base = work + ((size_t)j << P::LOGBUF);
+                const double2* gj = gp + (size_t)j * (k + 1) * o_stride;
+                double2 gv[P::KMAX + 1][RF];
+#pragma unroll
+                for (int o = 0; o <= P::KMAX; o++)
+                    if (o <= k) {
+#pragma unroll
+                        for (int m = 0; m < RF; m++) gv[o][m] = __ldg(gj + o * o_stride + m * NG);
+                    }
 #pragma unroll
                 for (int m = 0; m < RF; m++) x[m] = base[SW(w * RF + m)];
                 Dft<RF, false>::run(x);
-                const double2* gj = gp + (size_t)j * (k + 1) * o_stride;
 #pragma unroll
                 for (int o = 0; o <= P::KMAX; o++)
                     if (o <= k) {
 #pragma unroll
                         for (int m = 0; m < RF; m++) {
-                            const double2 v = __ldg(gj + o * o_stride + m * NG);
+                            const double2 v = gv[o][m];
                             r[o][m].x = fma(x[m].x, v.x, r[o][m].x);
                             r[o][m].x = fma(-x[m].y, v.y, r[o][m].x);
                             r[o][m].y = fma(x[m].x, v.y, r[o][m].y);
@@ -978,6 +1005,7 @@ k_cmux(u64* __restrict__ out, const u64* __restrict__ pool, const int* __restric
                         }
                     }
             }
+            // outputs overwrite buffers 0..k at the positions this thread alone reads: no barrier needed
 #pragma unroll
             for (int o = 0; o <= P::KMAX; o++)
                 if (o <= k) {
@@ -1060,7 +1088,7 @@ struct PbsLaunchArgs {
     u64* out; const u64* in; long B; const double2* bskF; const u64* luts; const int* lut_idx; long long* prof;
     size_t bsk_ct_stride;      // > 0: one GGSW list per ciphertext (k_pbs<P, true>)
     // batched CMUX
-    const u64* cm_pool; const int* cm_i0; const int* cm_i1; const int* cm_gi;
+    const u64* cm_pool; const int* cm_i0; const int* cm_i1; const int* cm_gi; int cm_plain;
     // bsk conversion
     double2* outF; const u64* bsk; long npoly;
     // polymul
@@ -1115,7 +1143,7 @@ struct PbsPlanOps {
     static int cmux(const PbsLaunchArgs& a) {
         const size_t smem = (size_t)a.g.J * P::BUF * 16 + (size_t)P::TW_SMEM * 16;
         return launch_clustered(k_cmux<P>, P::C, P::NT, P::TM_CTA, smem, a.B, a.st, a.out, a.cm_pool, a.cm_i0, a.cm_i1,
-                                a.bskF, a.cm_gi, a.B, a.g, a.twT, a.tw_mid);
+                                a.bskF, a.cm_gi, a.B, a.g, a.twT, a.tw_mid, a.cm_plain);
     }
     static int bsk(const PbsLaunchArgs& a) {
         const size_t smem = (size_t)P::BUF * 16 + (size_t)P::TW_SMEM * 16;

@@ -245,29 +245,46 @@ def _sign_bootstrap(ev, small: torch.Tensor, weights: Sequence[int], idx: Option
     return E.lin_add_plain(out, pt, p.ct_words)
 
 
-def extract_bits(ev, ct: torch.Tensor, m: int) -> List[torch.Tensor]:
-    """Bits (LSB first) of the cell index of residues mod m: small-key ciphertexts, phase in [0, 1/2) = 0."""
+def extract_bits_multi(ev, cts: Sequence[torch.Tensor], moduli: Sequence[int]) -> List[List[torch.Tensor]]:
+    """Bits (LSB first) of the cell index of every residue: per residue a list of small-key ciphertext batches whose
+    phase lies in [0, 1/2) for 0 and [1/2, 1) for 1.  Bit t of all residues is extracted together (one keyswitch and
+    one sign bootstrap launch per t), so the launches see r times the batch of a single residue."""
     p = ev.params
     L = p.ct_words
-    dev = ct.device
-    n_ct = ct.shape[0]
-    b, off, _, _ = block_layout(int(m))
+    dev = cts[0].device
+    n_ct = cts[0].shape[0]
+    lay = [block_layout(int(m)) for m in moduli]
 
-    def const(v):
-        return torch.full((n_ct,), _i64(v), dtype=torch.int64, device=dev)
+    def const(v, rows=n_ct):
+        return torch.full((rows,), _i64(v), dtype=torch.int64, device=dev)
 
-    buf = E.lin_add_plain(ct, const(off), L) if off else ct
-    bits = []
-    for t in range(b):
-        sh = E.lin_mul_clear(buf, const(1 << (b - 1 - t)), L) if b - 1 - t else buf
+    bufs = [E.lin_add_plain(ct, const(off), L) if off else ct for ct, (_, off, _, _) in zip(cts, lay)]
+    bits: List[List[torch.Tensor]] = [[] for _ in moduli]
+    for t in range(max(b for b, _, _, _ in lay)):
+        act = [i for i, (b, _, _, _) in enumerate(lay) if b > t]
+        sh = torch.cat([E.lin_mul_clear(bufs[i], const(1 << (lay[i][0] - 1 - t)), L) if lay[i][0] - 1 - t else bufs[i]
+                        for i in act], dim=0)
         ks = E.keyswitch(ev, sh)
         if t:
             # the removed lower bits leave a fraction in [0, 2^-t) of the half torus: centre it
-            ks = E.lin_add_plain(ks, const((1 << 62) - (1 << (62 - t))), p.n + 1)
-        bits.append(ks)
-        if t < b - 1:
-            buf = E.lin_sub(buf, _sign_bootstrap(ev, ks, [1 << (64 - b + t)], None), L)
+            ks = E.lin_add_plain(ks, const((1 << 62) - (1 << (62 - t)), ks.shape[0]), p.n + 1)
+        for j, i in enumerate(act):
+            bits[i].append(ks[j * n_ct:(j + 1) * n_ct])
+        more = [j for j, i in enumerate(act) if t < lay[i][0] - 1]
+        if more:
+            rows = ks if len(more) == len(act) else torch.cat([ks[j * n_ct:(j + 1) * n_ct] for j in more], dim=0)
+            weights = [1 << (64 - lay[act[j]][0] + t) for j in more]
+            idx = torch.arange(len(more), dtype=torch.int32, device=dev).repeat_interleave(n_ct)
+            got = _sign_bootstrap(ev, rows, weights, idx)
+            for q, j in enumerate(more):
+                i = act[j]
+                bufs[i] = E.lin_sub(bufs[i], got[q * n_ct:(q + 1) * n_ct], L)
     return bits
+
+
+def extract_bits(ev, ct: torch.Tensor, m: int) -> List[torch.Tensor]:
+    """Bits of the residues mod m in `ct` (see extract_bits_multi)."""
+    return extract_bits_multi(ev, [ct], [m])[0]
 
 
 def circuit_bootstrap(ev, bits: torch.Tensor) -> torch.Tensor:
@@ -332,7 +349,8 @@ def vertical_packing(ev, ggsw_f: torch.Tensor, n_ct: int, bits: int, pool: torch
             gi = (ar * bits + nrot + lvl).repeat_interleave(cnt).to(torch.int32).contiguous()
             out = torch.empty((n_ct * cnt, glwe), dtype=torch.int64, device=dev)
             _lib.call("fhe_cmux_batch", out.data_ptr(), cur_pool.data_ptr(), i0.data_ptr(), i1.data_ptr(),
-                      ggsw_f.data_ptr(), gi.data_ptr(), n_ct * cnt, k, N, p.cbs_level, p.cbs_base_log, E._stream())
+                      ggsw_f.data_ptr(), gi.data_ptr(), n_ct * cnt, k, N, p.cbs_level, p.cbs_base_log,
+                      1 if lvl == 0 else 0, E._stream())      # the leaves are plaintext polynomials
             cur_pool = out
             cur_idx = torch.arange(n_ct * cnt, dtype=torch.int64, device=dev).reshape(n_ct, cnt)
         acc_idx = cur_idx[:, 0].to(torch.int32).contiguous()
@@ -348,7 +366,23 @@ def vertical_packing(ev, ggsw_f: torch.Tensor, n_ct: int, bits: int, pool: torch
     return res
 
 
-WIDE_CHUNK = 256          # ciphertexts per pass: the GGSWs of a chunk take bits * cbs_level * (k+1)^2 * N * 16 B each
+PROFILE = None            # development aid: set to a dict to accumulate per-phase milliseconds (synchronises)
+_last_tick = [None]
+
+
+def _tick(name: str) -> None:
+    if PROFILE is None:
+        return
+    import time
+
+    torch.cuda.synchronize()
+    now = time.perf_counter()
+    if name != "start" and _last_tick[0] is not None:
+        PROFILE[name] = PROFILE.get(name, 0.0) + (now - _last_tick[0]) * 1e3
+    _last_tick[0] = now
+
+
+WIDE_CHUNK = 512          # ciphertexts per pass: the GGSWs of a chunk take bits * cbs_level * (k+1)^2 * N * 16 B each
 
 
 def wide_table_lookup(ev, cts: Sequence[torch.Tensor], pool: torch.Tensor, polys_per_residue: int,
@@ -364,16 +398,21 @@ def wide_table_lookup(ev, cts: Sequence[torch.Tensor], pool: torch.Tensor, polys
     for lo in range(0, n_all, WIDE_CHUNK):
         hi = min(n_all, lo + WIDE_CHUNK)
         n_ct = hi - lo
-        blist: List[torch.Tensor] = []
-        for ct, m in zip(cts, moduli):
+        parts = []
+        for ct in cts:
             part = ct[lo:hi]
             if not part.is_contiguous() or part.data_ptr() % 16:       # the linear kernels vectorise on 16 bytes
                 part = part.clone()
-            blist += extract_bits(ev, part, int(m))
+            parts.append(part)
+        _tick("start")
+        blist = [b for per_residue in extract_bits_multi(ev, parts, moduli) for b in per_residue]
         stacked = torch.stack(blist, dim=1).reshape(n_ct * bits, p.n + 1)          # [e][t]
+        _tick("extract")
         ggsw_f = circuit_bootstrap(ev, stacked)
+        _tick("circuit_bootstrap")
         tsel = torch.zeros(n_ct, dtype=torch.int64, device=stacked.device) if table_idx is None else table_idx[lo:hi].to(torch.int64)
         for o in range(r):
             first = (tsel * r + o) * polys_per_residue
             outs[o][lo:hi] = vertical_packing(ev, ggsw_f, n_ct, bits, pool, first)
+        _tick("vertical_packing")
     return outs

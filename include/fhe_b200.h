@@ -113,7 +113,8 @@ int fhe_pbs_batch_variant(uint64_t* out, const uint64_t* in, long B, const void*
  * fhe_blind_rotate_batch: the bootstrap's blind rotation + sample extraction with one list of n GGSWs per
  * ciphertext (ct_stride double2 elements apart) instead of a bootstrap key. */
 int fhe_cmux_batch(uint64_t* out, const uint64_t* pool, const int* i0, const int* i1, const void* ggsw_f,
-                   const int* gi, long B, int k, int N, int level, int base_log, void* stream);
+                   const int* gi, long B, int k, int N, int level, int base_log,
+                   int plain /* pool entries are plaintext polynomials (zero masks) */, void* stream);
 int fhe_blind_rotate_batch(uint64_t* out, const uint64_t* in, long B, const void* ggsw_f, long ct_stride,
                            const uint64_t* luts, const int* lut_idx, int n, int k, int N, int level,
                            int base_log, void* stream);

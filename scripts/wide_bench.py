@@ -27,6 +27,10 @@ for p_bits, n_ct in [(int(a.split(":")[0]), int(a.split(":")[1])) for a in (sys.
     outs = wide.wide_table_lookup(ev, cts, pool, polys)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    wide.PROFILE = {}
+    wide.wide_table_lookup(ev, cts, pool, polys)
+    prof, wide.PROFILE = wide.PROFILE, None
+    print("   phases (ms): " + ", ".join(f"{k} {v:.1f}" for k, v in prof.items()))
     res, errs = [], []
     for o, m in zip(outs, prm.moduli):
         _, ph = E.decrypt(ks, o, return_phase=True)

@@ -265,3 +265,18 @@ def test_linear_ops_bit_exact(oracle, cuda_device):
             gw[mm * Nc + nn] = W[:, nn]
     got = E.matmul_ct_clear(E.from_np_u64(x, cuda_device), torch.from_numpy(W).to(cuda_device), Mr, K, Nc, L)
     assert np.array_equal(E.to_np_u64(got), oracle.lin_gather_mac(x, gi, gw))
+
+
+def test_linear_ops_on_misaligned_row_slices(oracle, cuda_device):
+    """Row slices of [E, L] tensors with odd L start 8 bytes off a 16-byte boundary: the flat vectorised path
+    must not be taken for them (the CRT lanes of the wide path hand such slices around)."""
+    rng = np.random.default_rng(9)
+    L = 513
+    a = rng.integers(0, 1 << 63, (7, L), dtype=np.int64).astype(np.uint64)
+    b = rng.integers(0, 1 << 63, (7, L), dtype=np.int64).astype(np.uint64)
+    da, db = E.from_np_u64(a, cuda_device), E.from_np_u64(b, cuda_device)
+    for lo in (1, 2, 3):
+        sa, sb = da[lo:lo + 4], db[lo:lo + 4]
+        assert np.array_equal(E.to_np_u64(E.lin_add(sa, sb, L)), oracle.lin_add(a[lo:lo + 4], b[lo:lo + 4]))
+        assert np.array_equal(E.to_np_u64(E.lin_sub(sa, sb, L)), oracle.lin_sub(a[lo:lo + 4], b[lo:lo + 4]))
+        assert np.array_equal(E.to_np_u64(E.lin_neg(sa, L)), oracle.lin_neg(a[lo:lo + 4]))

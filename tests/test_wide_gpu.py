@@ -119,9 +119,24 @@ def test_cmux_batch_matches_oracle(oracle, setup, cuda_device):
     d_pool, d_i0, d_i1, d_gi = (E.from_np_u64(pool, cuda_device), torch.from_numpy(i0).to(cuda_device),
                                 torch.from_numpy(i1).to(cuda_device), torch.from_numpy(gi).to(cuda_device))
     _lib.call("fhe_cmux_batch", out.data_ptr(), d_pool.data_ptr(), d_i0.data_ptr(), d_i1.data_ptr(),
-              ggsw.data_ptr(), d_gi.data_ptr(), G, p.k, p.N, p.cbs_level, p.cbs_base_log,
+              ggsw.data_ptr(), d_gi.data_ptr(), G, p.k, p.N, p.cbs_level, p.cbs_base_log, 0,
               torch.cuda.current_stream().cuda_stream)
     got = E.to_np_u64(out)
+    # the plaintext-leaf shortcut (masks known to be zero) gives the same ciphertexts up to fp64 rounding
+    out_plain = torch.empty_like(out)
+    _lib.call("fhe_cmux_batch", out_plain.data_ptr(), d_pool.data_ptr(), d_i0.data_ptr(), d_i1.data_ptr(),
+              ggsw.data_ptr(), d_gi.data_ptr(), G, p.k, p.N, p.cbs_level, p.cbs_base_log, 1,
+              torch.cuda.current_stream().cuda_stream)
+    assert torus_dist(E.to_np_u64(out_plain), got).max() < 2.0 ** -40
+    # a second level on encrypted inputs (the outputs of the first): still selects the right polynomial
+    d_j0 = torch.tensor([0, 2], dtype=torch.int32, device=cuda_device)
+    d_j1 = torch.tensor([1, 3], dtype=torch.int32, device=cuda_device)
+    d_gj = torch.tensor([4, 5], dtype=torch.int32, device=cuda_device)
+    out2 = torch.empty((2, glwe), dtype=torch.int64, device=cuda_device)
+    _lib.call("fhe_cmux_batch", out2.data_ptr(), out.data_ptr(), d_j0.data_ptr(), d_j1.data_ptr(),
+              ggsw.data_ptr(), d_gj.data_ptr(), 2, p.k, p.N, p.cbs_level, p.cbs_base_log, 0,
+              torch.cuda.current_stream().cuda_stream)
+    got2 = E.to_np_u64(out2)
 
     def glwe_phase(ct):      # body - sum_j A_j * S_j (negacyclic), k = 1
         A, Bp = ct[:p.N], ct[p.N:]
@@ -132,6 +147,11 @@ def test_cmux_batch_matches_oracle(oracle, setup, cuda_device):
             acc[:j] += A[p.N - j:]
         return acc
 
+    first = [int(i1[b] if bitvals[b] else i0[b]) for b in range(G)]
+    for q in range(2):
+        sel = first[2 * q + 1] if bitvals[4 + q] else first[2 * q]
+        # encrypted inputs: the 18-bit rounding of the (uniform) mask is multiplied by the key, std ~ 2^-16.3
+        assert torus_dist(glwe_phase(got2[q]), pool[sel, p.k * p.N:]).max() < 2.0 ** -13
     for b in range(G):
         want = pool[i1[b] if bitvals[b] else i0[b], p.k * p.N:]
         ph, ph_ref = glwe_phase(got[b]), glwe_phase(ref[b])
