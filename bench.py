@@ -35,6 +35,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# DRAM bytes of one bootstrap launch of the bench workload, from the ncu capture named in traffic_note
+PBS_LAUNCH_DRAM_BYTES = 1058411829248 + 1190273792
 WORKLOAD = "cfg2_univariate8_64x64"
 CPU_SAMPLE_PBS = 16
 
@@ -284,10 +286,11 @@ def run_ours(args):
                        "l2_flush": "inputs (1.07 GB of ciphertexts per step) exceed the 126 MB L2",
                        "decrypted_output_correct": correct},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
-                         "traffic_note": "ncu --set full on a one-wave launch (15 ciphertexts): dram read 2.09 GB = the Fourier "
-                                         "BSK streamed once per wave (profiles/r01_pbs_p8_v3_ncu_summary.txt); a bench launch of "
-                                         "4096 ciphertexts is 274 such waves; fp64-bound kernel, HBM share of peak < 2 %",
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": PBS_LAUNCH_DRAM_BYTES,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_pbs launch of this workload "
+                                         "(4096 ciphertexts, ncu, profiles/r01_pbs_p8_dram_full_launch.csv): 1.058 TB read = the "
+                                         "2.09 GB Fourier BSK streamed ~1.85x per wave of 15 ciphertexts (274 waves; the clusters "
+                                         "drift apart), 1.2 GB written; 197 GB/s = 2.5 % of HBM peak -- the kernel is fp64-bound",
                          "kernel": "k_pbs", "launches_timed": n_pbs_launch, "mean_launch_ms": pbs_ms / max(n_pbs_launch, 1),
                          "flops_per_pbs": fl, "share_of_step": pbs_ms / ms if ms else None,
                          "peak_source": "DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no fp64 entry)"},

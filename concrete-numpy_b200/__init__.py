@@ -8,6 +8,7 @@ Layout:
   params.py        crypto-parameter selection + noise model (stands in for concrete-optimizer)
   keys.py          device-resident key sets, encrypt / decrypt
   mlir_text/       FHE / FHELinalg MLIR text: builder shim (`mlir`, `concrete.lang`) and parser
+  wide.py          9..16-bit values: CRT residues, bit extraction, circuit bootstrapping, vertical packing
   executor.py      walks the parsed program and launches the kernels
   compiler.py      `concrete.compiler`-compatible classes (JITSupport, ClientSupport, ...)
   api.py           Circuit / Client / Server mirror of the reference's compilation layer

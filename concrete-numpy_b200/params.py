@@ -247,8 +247,15 @@ def wide_lookup_flops(params: CryptoParams) -> float:
             + T * KS_MAC_COST * ks_macs(params.big_dim, params.n, params.ks_level) + packing + vp)
 
 
+WIDE_SHAPES = ((1, 2048), (1, 4096), (2, 1024), (3, 512))      # (k, N) candidates of the wide search
+# fraction of the k = 1, N = 2048 kernels' flop rate the bootstrap reaches at each shape (16-bit lookups on B200,
+# scripts/wide_bench.py: 7.0 / 3.5 / 2.5 TFLOP/s; profiles/r01_wide_lookup_bench.log): the search minimises time
+WIDE_SHAPE_EFFICIENCY = {(1, 2048): 1.0, (1, 4096): 0.9, (2, 1024): 0.5, (3, 512): 0.36}
+
+
 @lru_cache(maxsize=None)
-def select_wide_parameters(p: int, norm2: float = 1.0, p_error: float = 1e-9) -> CryptoParams:
+def select_wide_parameters(p: int, norm2: float = 1.0, p_error: float = 1e-9,
+                           shapes: tuple = WIDE_SHAPES) -> CryptoParams:
     """Cheapest parameter set for p-bit values (9..16) carried as CRT residues: every sign test of a lookup must
     hold with probability 1 - p_error / (number of extracted bits)."""
     from .wide import block_layout, crt_moduli, total_bits
@@ -263,7 +270,7 @@ def select_wide_parameters(p: int, norm2: float = 1.0, p_error: float = 1e-9) ->
     n_grid = np.arange(500, 1101, 12)
     lwe_var_grid = 4.0 ** np.maximum(SECURITY_SLOPE * n_grid + SECURITY_BIAS, MIN_LOG2_STD)
     ks_options = [(lv, b) for lv in range(1, 10) for b in range(1, 8) if lv * b <= 40]
-    for k, N in [(1, 2048), (1, 4096), (2, 1024), (3, 512)]:
+    for k, N in shapes:
         kN = k * N
         g2 = 4.0 ** secure_log2_std(kN)
         v_ms = (1.0 / 12.0 + n_grid / 24.0) / (4.0 * N * N)
@@ -310,6 +317,7 @@ def select_wide_parameters(p: int, norm2: float = 1.0, p_error: float = 1e-9) ->
                             if not np.any(ok):
                                 continue
                             cost = np.where(ok, base_cost + T * KS_MAC_COST * kN * (ks_level - 1) * (n_grid + 1), np.inf)
+                            cost = cost / WIDE_SHAPE_EFFICIENCY.get((k, N), 0.5)
                             j = int(np.argmin(cost))
                             if best is None or cost[j] < best[0]:
                                 best = (float(cost[j]), int(n_grid[j]), k, N, pbs_level, pbs_base_log, ks_level, ks_base_log,

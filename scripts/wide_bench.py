@@ -6,7 +6,8 @@ from concrete_numpy_b200 import engine as E, params as P, wide
 
 dev = torch.device("cuda:0")
 for p_bits, n_ct in [(int(a.split(":")[0]), int(a.split(":")[1])) for a in (sys.argv[1:] or ["16:256", "12:256", "9:256"])]:
-    prm = P.select_wide_parameters(p_bits, 1.0, 1e-6)
+    shapes = tuple(tuple(int(v) for v in t.split("x")) for t in os.environ["WIDE_SHAPES"].split(",")) if os.environ.get("WIDE_SHAPES") else P.WIDE_SHAPES
+    prm = P.select_wide_parameters(p_bits, 1.0, 1e-6, shapes)
     t0 = time.time()
     ks = E.KeySet(prm, dev, seed=5)
     ev = E.EvalKeys.of(ks)

@@ -63,3 +63,51 @@ def test_oracle_wide_lookup_decrypts_to_table(oracle):
     outs = W.wide_lookup(oracle, keys, cts, moduli, table)
     res = [W.decode_residue(oracle.decrypt_phase(o, keys.sk_big), m) for o, m in zip(outs, moduli)]
     assert np.array_equal(W.crt_combine(res, moduli), table[x])
+
+
+def test_wide_parameter_search_meets_its_own_error_budget():
+    from concrete_numpy_b200 import params as P
+
+    for p, norm2 in [(9, 1.0), (12, 4.0), (16, 1.0), (16, 256.0)]:
+        prm = P.select_wide_parameters(p, norm2, 1e-6)
+        assert prm.wide and prm.p == p and int(np.prod(prm.moduli)) >= 1 << p
+        assert P.pbs_cluster_size(prm.N, prm.k, prm.pbs_level) > 0 and P.pbs_cluster_size(prm.N, prm.k, prm.cbs_level) > 0
+        assert prm.pf_base_log <= 7                      # packing keyswitch stays on the exact int8 tensor-core path
+        assert P.estimate_wide_p_error(prm, norm2) <= 1e-6
+        assert abs(np.log2(prm.glwe_std) - P.secure_log2_std(prm.k * prm.N)) < 1e-9
+    with pytest.raises(ValueError):
+        P.select_wide_parameters(17)
+
+
+def test_wide_circuits_compile_with_crt_client_parameters():
+    """The reference frontend's MLIR for 9..16-bit circuits (tests/golden/wide_*.json) compiles to CRT parameters;
+    the client parameters announce the moduli where the reference's client looks for them (client.py:213-215)."""
+    import json
+
+    from golden_util import golden_names, load_golden
+    from concrete_numpy_b200 import compiler as cc
+
+    names = golden_names("wide_")
+    assert len(names) >= 6
+    for name in names:
+        doc = load_golden(name)
+        opt = cc.CompilationOptions.new("main")
+        opt.set_global_p_error(doc["global_p_error"])
+        res = cc.JITSupport.new().compile(doc["mlir"], opt)
+        assert res.crypto.wide and 9 <= res.crypto.p <= 16
+        cp = json.loads(res.client_parameters.serialize())
+        for gate in cp["inputs"] + cp["outputs"]:
+            if gate["encryption"] is not None:
+                assert gate["encryption"]["encoding"]["crt"] == list(res.crypto.moduli)
+        assert res.feedback.p_error <= 1e-4 and (res.feedback.complexity > 0 or res.info.n_pbs == 0)
+        # round trip of the parameter document (Server.save / load path)
+        assert cc.ClientParameters.unserialize(res.client_parameters.serialize()).crypto == res.crypto
+
+
+def test_analysis_reduces_weights_per_modulus():
+    from concrete_numpy_b200.executor import _centered
+
+    c = np.array([100, -7, 250, 9, 0, 13])
+    for m in (5, 7, 11, 13, 16):
+        r = _centered(c, m)
+        assert np.all((r - c) % m == 0) and r.min() >= -(m // 2) - (m % 2 == 0) * 0 and r.max() <= m // 2
