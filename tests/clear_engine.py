@@ -99,3 +99,71 @@ def table_lookup(ev, ct, luts, lut_idx=None):
     val = tables[which, np.where(neg, m - (1 << p), m)]
     val = np.where(neg, np.uint64(0) - val, val)
     return _t((val << np.uint64(63 - p))[:, None])
+
+
+# ---- wide integers (CRT residues): clear stand-ins for concrete_numpy_b200.wide.{lut_pool, wide_table_lookup} ----
+
+def wide_lut_pool(params, luts, device):
+    return _t(np.ascontiguousarray(luts))          # [tables, residues, 2^bits] encoded outputs
+
+
+def wide_table_lookup(ev, cts, pool, polys_per_residue, table_idx=None):
+    """Cell index of every residue word (what bit extraction reads) -> table pattern -> encoded output residues."""
+    from concrete_numpy_b200 import wide
+
+    moduli = ev.params.moduli
+    luts = _u(pool)
+    pattern = np.zeros(_u(cts[0]).shape[0], dtype=np.int64)
+    shift = 0
+    for ct, m in zip(cts, moduli):
+        b, off, _, _ = wide.block_layout(int(m))
+        phase = _u(ct)[:, -1] + np.uint64(off)
+        pattern |= (phase >> np.uint64(64 - b)).astype(np.int64) << shift
+        shift += b
+    sel = np.zeros(pattern.size, dtype=np.int64) if table_idx is None else table_idx.numpy().astype(np.int64)
+    return [_t(luts[sel, o, pattern][:, None]) for o in range(len(moduli))]
+
+
+def install_wide(monkeypatch_or_none=None):
+    """Route the executor's wide lookups to the clear stand-ins (CPU tests of the CRT lanes)."""
+    from concrete_numpy_b200 import wide
+
+    if monkeypatch_or_none is None:
+        wide.lut_pool, wide.wide_table_lookup = wide_lut_pool, wide_table_lookup
+    else:
+        monkeypatch_or_none.setattr(wide, "lut_pool", wide_lut_pool)
+        monkeypatch_or_none.setattr(wide, "wide_table_lookup", wide_table_lookup)
+
+
+def run_crt(X, doc, args, group=None):
+    """Execute a golden circuit on clear CRT residues: client encoding (compiler.encrypt_arguments), executor lanes,
+    client decoding (compiler.decrypt_result + api.Client.decrypt) without the encryption."""
+    from concrete_numpy_b200 import wide
+    from concrete_numpy_b200.engine import CryptoParams
+    from concrete_numpy_b200.mlir_text.parser import parse_module
+
+    program = parse_module(doc["mlir"])
+    p = X.analyze(program).precision
+    moduli = wide.crt_moduli(p)
+    params = CryptoParams(p=p, n=1, k=0, N=1 << 11, pbs_level=1, pbs_base_log=1, ks_level=1, ks_base_log=1,
+                          lwe_std=0.0, glwe_std=0.0, moduli=moduli, cbs_level=1, cbs_base_log=1, pf_level=1, pf_base_log=1)
+    ex = X.Executor(program, params, "cpu", group=group)
+    vals = []
+    for (_, t), a, signed in zip(program.args, args, doc["input_signs"]):
+        a = np.asarray(a, dtype=np.int64)
+        if t.encrypted:
+            off = (1 << (t.width - 1)) if signed else 0
+            pts = np.concatenate([wide.encode_residue((a + off).reshape(-1), m) for m in moduli])
+            vals.append(X.Ct(_t(pts[:, None]), t.dims))
+        else:
+            vals.append(a)
+    outs = ex.run(ClearEval(params), vals)
+    M = int(np.prod([int(m) for m in moduli], dtype=object))
+    res = []
+    for o, t, signed in zip(outs, program.result_types, doc["output_signs"]):
+        per = _u(o.data)[:, -1].reshape(len(moduli), -1)
+        m = wide.crt_combine([wide.decode_residue(per[i], mod) for i, mod in enumerate(moduli)], moduli)
+        if signed:
+            m = np.where(m < M // 2, m, m - M)
+        res.append(int(m[0]) if t.dims == () else m.reshape(t.dims))
+    return res[0] if len(res) == 1 else tuple(res)

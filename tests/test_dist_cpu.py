@@ -51,6 +51,14 @@ def _worker(rank, world, port, names, failures):
                 got = res[0] if len(res) == 1 else tuple(res)
                 if not same(got, to_value(case["expected"])):
                     failures.put((rank, name))
+        # wide integers: every rank looks up its slice of the elements of all residues, then all-gathers per residue
+        clear_engine.install_wide()
+        for name in ("wide_matmul_relu_14bit", "wide_multi_table_9bit", "wide_linear_tlu_16bit"):
+            doc = load_golden(name)
+            for case in doc["cases"]:
+                got = clear_engine.run_crt(X, doc, [to_value(a) for a in case["args"]], group=dist.group.WORLD)
+                if not same(got, to_value(case["expected"])):
+                    failures.put((rank, name))
     finally:
         dist.destroy_process_group()
 

@@ -62,3 +62,17 @@ def test_pbs_counts_match_survey(clear_backend):
     for name, (n_pbs, depth, p) in expect.items():
         info = X.analyze(parse_module(load_golden(name)["mlir"]))
         assert (info.n_pbs, info.tlu_depth, info.precision) == (n_pbs, depth, p), name
+
+
+WIDE = golden_names("wide_")
+
+
+@pytest.mark.parametrize("name", WIDE)
+def test_golden_wide_crt_lanes(name, clear_backend, monkeypatch):
+    """9..16-bit circuits on clear CRT residues: residue encodings, per-residue weight reduction, lane execution,
+    table expansion over the extracted-bit patterns and CRT decoding reproduce the reference's clear evaluation."""
+    clear_engine.install_wide(monkeypatch)
+    doc = load_golden(name)
+    for case in doc["cases"]:
+        got = clear_engine.run_crt(X, doc, [to_value(a) for a in case["args"]])
+        assert same(got, to_value(case["expected"])), name
