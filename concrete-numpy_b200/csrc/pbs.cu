@@ -44,16 +44,28 @@ static std::vector<int> fitting_plans(int N, int k, int level) {
     const int logN = ilog2_exact(N);
     if (logN < 8 || logN > 15 || k < 1 || k > 3 || level < 1 || level > 4) return out;
     const int logM = logN - 1;
-    for (int C = 1; C <= 16; C *= 2)
+    // one plan per cluster size: the one that keeps the most threads resident per SM for this (k, level)
+    // (shared memory, the 64K-register file at 255 registers per thread, tensor-memory columns); ties go to the
+    // earlier entry
+    for (int C = 1; C <= 16; C *= 2) {
+        int best = -1;
+        long best_threads = 0;
         for (size_t i = 0; i < plans.size(); i++) {
             const PbsPlanMeta& m = plans[i].meta;
             if (m.C != C || m.logM != logM) continue;
             if (k > m.kmax || (k <= 1 && m.kmax > 1)) continue;
-            if (plan_smem(m, k, level) > PBS_SMEM_MAX) continue;
-            bool dup = false;                      // one plan per cluster size
-            for (int j : out) dup |= (plans[j].meta.C == C);
-            if (!dup) out.push_back((int)i);
+            const size_t smem = plan_smem(m, k, level);
+            if (smem > PBS_SMEM_MAX) continue;
+            long ctas = (long)(233472 / (smem + 1024));
+            const long by_regs = 256 / m.NT > 0 ? 256 / m.NT : 1;
+            if (ctas > by_regs) ctas = by_regs;
+            if (m.minb == 1 && ctas > 1) ctas = 1;            // tensor-memory twiddle plans are built for one CTA per SM
+            if (ctas < 1) ctas = 1;
+            const long threads = ctas * m.NT;
+            if (threads > best_threads) { best_threads = threads; best = (int)i; }
         }
+        if (best >= 0) out.push_back(best);
+    }
     return out;
 }
 
@@ -181,6 +193,17 @@ int fhe_pbs_variant_cluster_size(int N, int k, int level, int variant) {
     const std::vector<int> fit = fitting_plans(N, k, level);
     if (variant < 0 || variant >= (int)fit.size()) return -1;
     return plans[fit[variant]].meta.C;
+}
+
+// plan parameters of a variant: meta[0..7] = C, log2 R1, log2 RA, log2 RB, log2 RF, threads, min CTAs/SM, k max
+int fhe_pbs_variant_plan(int N, int k, int level, int variant, int* meta) {
+    static const std::vector<PbsPlanEntry> plans = all_plans();
+    const std::vector<int> fit = fitting_plans(N, k, level);
+    if (variant < 0 || variant >= (int)fit.size() || !meta) return -1;
+    const PbsPlanMeta& m = plans[fit[variant]].meta;
+    const int v[8] = {m.C, m.logR1, m.lra, m.lrb, m.lrf, m.NT, m.minb, m.kmax};
+    for (int i = 0; i < 8; i++) meta[i] = v[i];
+    return 0;
 }
 
 // how many ciphertexts variant `variant` bootstraps concurrently on the current device (one wave)

@@ -40,7 +40,7 @@ def secure_log2_std(dim: int) -> float:
 _PBS_PLANS = [
     (1, 9, 3, 0, 3, 1, 2), (1, 8, 3, 0, 3, 1, 2), (1, 7, 3, 0, 3, 1, 1),
     (1, 7, 3, 0, 2, 3, 1), (1, 8, 3, 0, 2, 3, 1), (1, 9, 3, 0, 2, 3, 1), (1, 10, 4, 0, 2, 3, 1),
-    (2, 12, 4, 4, 3, 1, 1), (2, 11, 4, 3, 3, 1, 2), (1, 11, 4, 0, 3, 1, 1), (1, 10, 4, 0, 3, 1, 2),
+    (2, 12, 4, 4, 3, 1, 1), (2, 11, 4, 3, 3, 1, 2), (1, 11, 4, 0, 3, 1, 1), (1, 10, 4, 0, 3, 1, 2), (1, 10, 4, 0, 3, 1, 1),
     (16, 14, 4, 3, 3, 1, 2), (8, 14, 4, 4, 3, 1, 1), (8, 13, 4, 3, 3, 1, 2), (4, 13, 4, 4, 3, 1, 1), (4, 12, 4, 3, 3, 1, 2),
 ]
 

@@ -91,6 +91,9 @@ int fhe_pbs_batch(uint64_t* out /* [B][kN+1] */, const uint64_t* in /* [B][n+1] 
  * fhe_bsk_relayout permutes a key from one variant's layout into another's (same spectrum values). */
 int fhe_pbs_num_variants(int N, int k, int level);
 int fhe_pbs_variant_cluster_size(int N, int k, int level, int variant);
+/* plan of a variant: meta[0..7] = cluster size, log2 of the stage-1 / mid-pass A / mid-pass B / fused radices,
+ * threads per CTA, minimum CTAs per SM, largest GLWE dimension (documentation / tests) */
+int fhe_pbs_variant_plan(int N, int k, int level, int variant, int* meta);
 /* ciphertexts the variant bootstraps concurrently on the current device (one wave of clusters) */
 int fhe_pbs_variant_capacity(int N, int k, int level, int variant);
 int fhe_bsk_to_fourier_variant(void* bsk_f, const uint64_t* bsk_std, int n, int k, int N, int level,
