@@ -41,6 +41,7 @@ _SIGS = {
     "fhe_bsk_to_fourier_variant": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_bsk_relayout": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_pbs_batch_variant": (C.c_int, [_p, _p, C.c_long, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
+    "fhe_pbs_batch_multi": (C.c_int, [_p, _p, C.c_long, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_cmux_batch": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_blind_rotate_batch": (C.c_int, [_p, _p, C.c_long, _p, C.c_long, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_pbs_set_profile": (C.c_int, [_p]),

@@ -131,6 +131,8 @@ static int get_plan(int n, int k, int N, int level, int base_log, int variant, c
     g.logN = logN; g.logM = logN - 1;
     g.J = (k + 1) * level;
     g.inv_M = 1.0 / (double)(N / 2);
+    g.theta = 0;
+    g.nout = 1;
     {
         const char* e = getenv("FHE_PBS_STAGGER");
         g.stagger = e ? atoi(e) : 0;
@@ -294,6 +296,26 @@ int fhe_blind_rotate_batch(u64* out, const u64* in, long B, const double2* ggsw_
     a.st = (cudaStream_t)stream;
     a.out = out; a.in = in; a.B = B; a.bskF = ggsw_f; a.luts = luts; a.lut_idx = lut_idx;
     a.bsk_ct_stride = (size_t)ct_stride;
+    return e->pbs(a);
+}
+
+// Multi-output bootstrap (Chillotti, Ligier, Orfila, Tap, "Improved programmable bootstrapping with larger precision
+// and efficient arithmetic circuits for TFHE", 2021, PBSmanyLUT): the modulus switch keeps `theta` zero low bits, the
+// accumulators interleave up to 2^theta functions (coefficient i belongs to function i mod 2^theta) and coefficients
+// 0..nout-1 of the rotated accumulator are extracted: out [B][nout][kN+1].  One blind rotation for nout results on the
+// same input, at the price of 2^theta times the modulus-switch noise.
+int fhe_pbs_batch_multi(u64* out, const u64* in, long B, const double2* bsk_f, const u64* luts, const int* lut_idx,
+                        int n, int k, int N, int level, int base_log, int theta, int nout, int variant, void* stream) {
+    if (B < 0 || theta < 0 || theta > 4 || nout < 1 || nout > (1 << theta)) FHE_FAIL(2, "pbs_batch_multi: bad arguments");
+    if (B == 0) return 0;
+    PbsLaunchArgs a = {};
+    const PbsPlanEntry* e = nullptr;
+    int rc = get_plan(n, k, N, level, base_log, variant, &e, &a);
+    if (rc) return rc;
+    a.st = (cudaStream_t)stream;
+    a.out = out; a.in = in; a.B = B; a.bskF = bsk_f; a.luts = luts; a.lut_idx = lut_idx;
+    a.g.theta = theta;
+    a.g.nout = nout;
     return e->pbs(a);
 }
 

@@ -40,6 +40,10 @@ struct PbsGeom {
     int dbg;              // development ablation bits (FHE_PBS_DBG), 0 in production
     long long* prof;      // phase-cycle buffer (fhe_pbs_set_profile) or null
     int stagger;          // start-up delay per cluster id (SM cycles), de-synchronises the clusters' phases
+    // extended bootstrap (k_pbs<P, true>): the modulus switch keeps `theta` zero low bits, so one blind rotation
+    // serves 2^theta interleaved test polynomials and coefficients 0..nout-1 are extracted (nout <= 2^theta);
+    // 0 / 1 for a plain bootstrap
+    int theta, nout;
     double2 cj[16];       // exp(i*pi*j1/(2*R1)), j1 < R1
 };
 
@@ -275,6 +279,12 @@ __device__ __forceinline__ int modswitch(u64 x, int logN) {  // -> Z_{2N}
     const int lg = logN + 1;
     u64 t = ((x >> (64 - lg - 1)) + 1) >> 1;
     return (int)(t & ((1ULL << lg) - 1));
+}
+// -> multiples of 2^theta in Z_{2N} (rounded): the rotation leaves the low theta bits of every index alone
+__device__ __forceinline__ int modswitch_coarse(u64 x, int logN, int theta) {
+    const int lg = logN + 1 - theta;
+    u64 t = ((x >> (64 - lg - 1)) + 1) >> 1;
+    return (int)((t & ((1ULL << lg) - 1)) << theta);
 }
 
 // ---- per-thread twiddle factors in tensor memory -------------------------------------------------
@@ -576,9 +586,12 @@ __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* _
 }
 
 // ---- the bootstrap kernel ------------------------------------------------------------------
-// PERCT: every ciphertext brings its own list of n Fourier GGSWs (bsk_ct_stride double2 apart) -- the blind
-// rotation of the wide-integer lookup, where the GGSWs come out of circuit bootstrapping (wide.py)
-template <class P, bool PERCT = false>
+// EXT (extended bootstrap, used by the wide-integer lookup, wide.py):
+//  * bsk_ct_stride > 0: every ciphertext brings its own list of n Fourier GGSWs (bsk_ct_stride double2 apart) --
+//    the blind rotation of vertical packing, where the GGSWs come out of circuit bootstrapping;
+//  * g.theta / g.nout: one blind rotation evaluates up to 2^theta test polynomials interleaved in the accumulator
+//    (coefficient i belongs to function i mod 2^theta) and extracts coefficients 0..nout-1 (out: [B][nout][kN+1]).
+template <class P, bool EXT = false>
 __global__ void __launch_bounds__(P::NT, P::MINB)
 k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* __restrict__ bskF_all,
       const u64* __restrict__ luts, const int* __restrict__ lut_idx, const PbsGeom g,
@@ -628,12 +641,12 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
     }
 
     for (long ct = cluster_id; ct < B; ct += nclusters) {
-        const double2* bskF = PERCT ? bskF_all + (size_t)ct * bsk_ct_stride : bskF_all;
+        const double2* bskF = EXT ? bskF_all + (size_t)ct * bsk_ct_stride : bskF_all;
         const u64* lwe = in + (size_t)ct * (g.n + 1);
         const u64* lut = luts + (size_t)(lut_idx ? lut_idx[ct] : 0) * (k + 1) * N;
         // ---- ACC = X^{-b~} * LUT
         {
-            const int a0 = (2 * N - modswitch(lwe[g.n], g.logN)) & (2 * N - 1);
+            const int a0 = (2 * N - (EXT ? modswitch_coarse(lwe[g.n], g.logN, g.theta) : modswitch(lwe[g.n], g.logN))) & (2 * N - 1);
             for (int w = tid; w < (k + 1) * S; w += NT) {
                 const int c = w >> P::LOGS, s = w & (S - 1);
                 const int v = (slot_to_coef<P>(s, rank) - a0) & (2 * N - 1);
@@ -641,12 +654,12 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
                 acc[w] = (v >> (P::LOGM + 1)) ? (0ULL - x) : x;
             }
         }
-        int a_next = modswitch(lwe[0], g.logN);
+        int a_next = EXT ? modswitch_coarse(lwe[0], g.logN, g.theta) : modswitch(lwe[0], g.logN);
         csync<C>();
 
         for (int i = 0; i < g.n; i++) {
             const int a = a_next;
-            a_next = (i + 1 < g.n) ? modswitch(lwe[i + 1], g.logN) : 0;
+            a_next = (i + 1 < g.n) ? (EXT ? modswitch_coarse(lwe[i + 1], g.logN, g.theta) : modswitch(lwe[i + 1], g.logN)) : 0;
             // GGSW_{i+1} slices of this rank -> L2 one iteration ahead (HBM latency off the MAC's path)
             if (i + 1 < g.n && tid < J * (k + 1) && !(g.dbg & 16))
                 prefetch_l2_bulk(bskF + (size_t)(i + 1) * ggsw_stride + (((size_t)tid * C + rank) << P::LOGBUF),
@@ -767,8 +780,8 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
             csync<C>();
             PBS_PROF(7)
         }
-        // ---- sample extract coefficient 0
-        {
+        // ---- sample extract coefficient 0 (extended: coefficients 0..nout-1)
+        if (!EXT) {
             u64* o = out + (size_t)ct * ((size_t)k * N + 1);
             for (int w = tid; w < (k + 1) * S; w += NT) {
                 const int c = w >> P::LOGS, s = w & (S - 1);
@@ -779,6 +792,22 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
                     else o[(size_t)c * N + (N - j)] = 0ULL - v;
                 } else if (j == 0)
                     o[(size_t)k * N] = v;
+            }
+        } else {
+            const int nout = g.nout;
+            for (int u = 0; u < nout; u++) {
+                // coefficient u of the product: mask word t of polynomial c is A_c[u - t] (t <= u), -A_c[N + u - t] (t > u)
+                u64* o = out + ((size_t)ct * nout + u) * ((size_t)k * N + 1);
+                for (int w = tid; w < (k + 1) * S; w += NT) {
+                    const int c = w >> P::LOGS, s = w & (S - 1);
+                    const int j = slot_to_coef<P>(s, rank);
+                    const u64 v = acc[w];
+                    if (c < k) {
+                        if (j <= u) o[(size_t)c * N + (u - j)] = v;
+                        else o[(size_t)c * N + (N + u - j)] = 0ULL - v;
+                    } else if (j == u)
+                        o[(size_t)k * N] = v;
+                }
             }
         }
         // the same thread re-initialises the same ACC words at the top of the loop
@@ -1134,7 +1163,7 @@ struct PbsPlanOps {
         return per_sm * sms;
     }
     static int pbs(const PbsLaunchArgs& a) {
-        if (a.bsk_ct_stride)
+        if (a.bsk_ct_stride || a.g.nout > 1 || a.g.theta > 0)
             return launch_clustered(k_pbs<P, true>, P::C, P::NT, P::TM_CTA, smem_pbs(a.g), a.B, a.st, a.out, a.in, a.B,
                                     a.bskF, a.luts, a.lut_idx, a.g, a.twT, a.tw_mid, a.prof, a.bsk_ct_stride);
         return launch_clustered(k_pbs<P, false>, P::C, P::NT, P::TM_CTA, smem_pbs(a.g), a.B, a.st, a.out, a.in, a.B, a.bskF,

@@ -87,8 +87,9 @@ def variance_keyswitch(kN, level, base_log, lwe_var):
     return kN * level * (B2 + 2.0) / 12.0 * lwe_var + kN / 2.0 / (12.0 * 4.0 ** (base_log * level))
 
 
-def variance_modswitch(n, N):
-    return (1.0 / 12.0 + n / 24.0) / (4.0 * N * N)
+def variance_modswitch(n, N, theta=0):
+    """theta > 0: the multi-output bootstrap switches to 2N / 2^theta levels (fhe_pbs_batch_multi)."""
+    return (1.0 / 12.0 + n / 24.0) / (4.0 * N * N) * 4.0 ** theta
 
 
 def p_error_of(p, variance):
@@ -216,8 +217,10 @@ def wide_sign_tests(params: CryptoParams, norm2: float):
     g2 = params.glwe_std ** 2
     v_pbs = variance_pbs_out(params.n, params.k, params.N, params.pbs_level, params.pbs_base_log, g2)
     v_in = max(wide_output_variance(params), g2) * max(norm2, 1.0)
+    from .wide import bootstrap_theta
+
     v_small = (variance_keyswitch(params.big_dim, params.ks_level, params.ks_base_log, params.lwe_std ** 2)
-               + variance_modswitch(params.n, params.N))
+               + variance_modswitch(params.n, params.N, bootstrap_theta(params)))
     tests = []
     for m in params.moduli:
         b, _, _, cells = block_layout(int(m))
@@ -237,7 +240,7 @@ def wide_lookup_flops(params: CryptoParams) -> float:
     from .wide import PF_PAD, block_bits, total_bits
 
     T = total_bits(params.moduli)
-    n_boot = sum(block_bits(int(m)) - 1 for m in params.moduli) + T * params.cbs_level
+    n_boot = T                     # one multi-output bootstrap per extracted bit
     M = params.N / 2
     ext = ((params.k + 1) * (params.cbs_level + 1) * 5 * M * math.log2(M) + 8 * (params.k + 1) ** 2 * params.cbs_level * M)
     logN = params.N.bit_length() - 1
@@ -291,6 +294,7 @@ def select_wide_parameters(p: int, norm2: float = 1.0, p_error: float = 1e-9,
                 for cbs_level in (1, 2, 3, 4):
                     if pbs_cluster_size(N, k, cbs_level) < 0:
                         continue
+                    v_ms_multi = v_ms * 4.0 ** max(1, cbs_level.bit_length())      # coarse modulus switch
                     for cbs_base_log in range(2, 16):
                         if cbs_level * cbs_base_log > 40:
                             break
@@ -301,7 +305,7 @@ def select_wide_parameters(p: int, norm2: float = 1.0, p_error: float = 1e-9,
                         for b, _, _, cells in lay:
                             for t in range(b):
                                 margin = cells / 2.0 if t == 0 else 0.25 * (1.0 - 2.0 ** -t)
-                                budget = np.minimum(budget, (margin / z) ** 2 - 4.0 ** (b - 1 - t) * (v_in + t * v_pbs) - v_ms)
+                                budget = np.minimum(budget, (margin / z) ** 2 - 4.0 ** (b - 1 - t) * (v_in + t * v_pbs) - v_ms_multi)
                         if not np.any(budget > 0):
                             continue
                         probe = CryptoParams(p=p, n=int(n_grid[0]), k=k, N=N, pbs_level=pbs_level, pbs_base_log=pbs_base_log,

@@ -10,11 +10,13 @@ algorithm on top of the C ABI:
 
   value x  ->  residues x mod m_i, each one LWE ciphertext of phase (x mod m_i) * 2^64 / m_i (no padding bit);
                add / sub / neg / clear multiplication act residue-wise on the torus (mod m_i for free)
-  lookup   ->  1. bit extraction per residue   keyswitch + sign bootstrap per bit      fhe_keyswitch_batch*, fhe_pbs_batch*
-               2. circuit bootstrapping        cbs_level sign bootstraps per bit, then ONE packing keyswitch with
-                                               (k+1)^2 N columns (all k+1 private functional keyswitches at once:
-                                               the key is the bootstrap-key construction applied to the extended
-                                               big key (s, -1)), Fourier conversion        fhe_bsk_to_fourier
+  lookup   ->  1. bit extraction per residue   keyswitch + ONE multi-output sign bootstrap per bit (the bit's weight
+                                               for the subtraction and its cbs_level gadget levels come out of the
+                                               same blind rotation)                    fhe_keyswitch_batch*, fhe_pbs_batch_multi
+               2. circuit bootstrapping        per level ONE packing keyswitch with (k+1)^2 N columns (all k+1
+                                               private functional keyswitches at once: the key is the bootstrap-key
+                                               construction applied to the extended big key (s, -1)),
+                                               Fourier conversion                       fhe_bsk_to_fourier
                3. vertical packing             CMUX tree over the high bits            fhe_cmux_batch
                                                blind rotation by the low log2(N) bits  fhe_blind_rotate_batch
              one pass of step 3 per output residue; steps 1-2 are shared.
@@ -229,26 +231,48 @@ def _const_accumulators(params, values: Sequence[int], device) -> torch.Tensor:
     return E.from_np_u64(acc, device)
 
 
-def _sign_bootstrap(ev, small: torch.Tensor, weights: Sequence[int], idx: Optional[torch.Tensor]) -> torch.Tensor:
-    """phase in [0, 1/2) -> 0, [1/2, 1) -> weights[idx[e]]: bootstrap with the constant test polynomial -w/2, then
-    + w/2 on the body."""
+def bootstrap_theta(params) -> int:
+    """log2 of the functions one blind rotation of the lookup evaluates (fhe_pbs_batch_multi): the extraction weight
+    of a bit plus its cbs_level circuit-bootstrap levels."""
+    return max(1, int(params.cbs_level).bit_length())
+
+
+def sign_bootstrap_multi(ev, small: torch.Tensor, ext_weights: Sequence[int], idx: torch.Tensor) -> torch.Tensor:
+    """One blind rotation per row of `small` (phase in [0, 1/2) = bit 0, [1/2, 1) = bit 1) -> [R, 1 + cbs_level, kN+1]:
+    bit * ext_weights[idx[e]] and bit * 2^(64-(lv+1)*cbs_base_log).  Function u owns the accumulator coefficients
+    congruent to u mod 2^theta (constant -w_u/2); + w_u/2 on the bodies afterwards."""
     p = ev.params
     dev = small.device
-    key = ("sign", tuple(weights))
-    cache = ev.wide_cache
-    if key not in cache:
-        cache[key] = (_const_accumulators(p, [-(w >> 1) for w in weights], dev),
-                      torch.tensor([_i64(w >> 1) for w in weights], dtype=torch.int64, device=dev))
-    luts, half = cache[key]
-    out = E.bootstrap(ev, small, luts, idx)
-    pt = half[idx.long()] if idx is not None else half[:1].expand(out.shape[0]).contiguous()
-    return E.lin_add_plain(out, pt, p.ct_words)
+    theta, nout = bootstrap_theta(p), 1 + p.cbs_level
+    key = ("msign", tuple(ext_weights))
+    if key not in ev.wide_cache:
+        cbs_w = [1 << (64 - (lv + 1) * p.cbs_base_log) for lv in range(p.cbs_level)]
+        acc = np.zeros((len(ext_weights), (p.k + 1) * p.N), dtype=np.uint64)
+        half = np.zeros((len(ext_weights), nout), dtype=np.int64)
+        for a, w in enumerate(ext_weights):
+            for u, wu in enumerate([w] + cbs_w):
+                acc[a, p.k * p.N + u::1 << theta] = np.uint64((-(wu >> 1)) % (1 << 64))
+                half[a, u] = _i64(wu >> 1)
+        ev.wide_cache[key] = (E.from_np_u64(acc, dev), torch.from_numpy(half).to(dev))
+    luts, half = ev.wide_cache[key]
+    R = small.shape[0]
+    out = torch.empty((R, nout, p.ct_words), dtype=torch.int64, device=dev)
+    v = ev.variant_for_batch(R)
+    with torch.cuda.device(dev):
+        _lib.call("fhe_pbs_batch_multi", out.data_ptr(), small.data_ptr(), R, ev.bsk_for_variant(v).data_ptr(),
+                  luts.data_ptr(), idx.data_ptr(), p.n, p.k, p.N, p.pbs_level, p.pbs_base_log, theta, nout, v, E._stream())
+    pt = half[idx.long()].reshape(-1).contiguous()
+    return E.lin_add_plain(out.view(R * nout, p.ct_words), pt, p.ct_words).view(R, nout, p.ct_words)
 
 
-def extract_bits_multi(ev, cts: Sequence[torch.Tensor], moduli: Sequence[int]) -> List[List[torch.Tensor]]:
-    """Bits (LSB first) of the cell index of every residue: per residue a list of small-key ciphertext batches whose
-    phase lies in [0, 1/2) for 0 and [1/2, 1) for 1.  Bit t of all residues is extracted together (one keyswitch and
-    one sign bootstrap launch per t), so the launches see r times the batch of a single residue."""
+def extract_and_bootstrap(ev, cts: Sequence[torch.Tensor], moduli: Sequence[int]):
+    """Bits (LSB first) of the cell index of every residue.  Returns (bits, levels), one list per residue: the
+    small-key ciphertexts that were tested (phase in [0, 1/2) = 0; kept for tests) and, per bit, the cbs_level LWEs
+    bit * 2^(64-(lv+1)*b) under the big key, [E, cbs_level, kN+1].
+
+    Bit t of all residues goes through one keyswitch and one multi-output bootstrap launch; the bit is subtracted
+    from the residue with the result of the SAME blind rotation that feeds circuit bootstrapping, so the two can
+    never disagree on a residue sitting on a cell boundary."""
     p = ev.params
     L = p.ct_words
     dev = cts[0].device
@@ -260,6 +284,7 @@ def extract_bits_multi(ev, cts: Sequence[torch.Tensor], moduli: Sequence[int]) -
 
     bufs = [E.lin_add_plain(ct, const(off), L) if off else ct for ct, (_, off, _, _) in zip(cts, lay)]
     bits: List[List[torch.Tensor]] = [[] for _ in moduli]
+    levels: List[List[torch.Tensor]] = [[] for _ in moduli]
     for t in range(max(b for b, _, _, _ in lay)):
         act = [i for i, (b, _, _, _) in enumerate(lay) if b > t]
         sh = torch.cat([E.lin_mul_clear(bufs[i], const(1 << (lay[i][0] - 1 - t)), L) if lay[i][0] - 1 - t else bufs[i]
@@ -268,38 +293,28 @@ def extract_bits_multi(ev, cts: Sequence[torch.Tensor], moduli: Sequence[int]) -
         if t:
             # the removed lower bits leave a fraction in [0, 2^-t) of the half torus: centre it
             ks = E.lin_add_plain(ks, const((1 << 62) - (1 << (62 - t)), ks.shape[0]), p.n + 1)
+        weights = [1 << (64 - lay[i][0] + t) for i in act]
+        idx = torch.arange(len(act), dtype=torch.int32, device=dev).repeat_interleave(n_ct)
+        got = sign_bootstrap_multi(ev, ks, weights, idx)                 # [len(act) * n_ct, 1 + lc, L]
         for j, i in enumerate(act):
+            part = got[j * n_ct:(j + 1) * n_ct]
             bits[i].append(ks[j * n_ct:(j + 1) * n_ct])
-        more = [j for j, i in enumerate(act) if t < lay[i][0] - 1]
-        if more:
-            rows = ks if len(more) == len(act) else torch.cat([ks[j * n_ct:(j + 1) * n_ct] for j in more], dim=0)
-            weights = [1 << (64 - lay[act[j]][0] + t) for j in more]
-            idx = torch.arange(len(more), dtype=torch.int32, device=dev).repeat_interleave(n_ct)
-            got = _sign_bootstrap(ev, rows, weights, idx)
-            for q, j in enumerate(more):
-                i = act[j]
-                bufs[i] = E.lin_sub(bufs[i], got[q * n_ct:(q + 1) * n_ct], L)
-    return bits
+            levels[i].append(part[:, 1:])
+            if t < lay[i][0] - 1:
+                bufs[i] = E.lin_sub(bufs[i], part[:, 0].contiguous(), L)
+    return bits, levels
 
 
-def extract_bits(ev, ct: torch.Tensor, m: int) -> List[torch.Tensor]:
-    """Bits of the residues mod m in `ct` (see extract_bits_multi)."""
-    return extract_bits_multi(ev, [ct], [m])[0]
-
-
-def circuit_bootstrap(ev, bits: torch.Tensor) -> torch.Tensor:
-    """bits [G, n+1] -> Fourier GGSWs (G * fhe_bsk_fourier_elems(1, ...) complex values, vertical-packing plan)."""
+def circuit_bootstrap(ev, lwe: torch.Tensor) -> torch.Tensor:
+    """lwe [G, cbs_level, kN+1] (bit * gadget factor per level) -> Fourier GGSWs (G * fhe_bsk_fourier_elems(1, ...)
+    complex values, plan of the vertical-packing external products): one packing keyswitch row per level."""
     p = ev.params
-    G = bits.shape[0]
-    dev = bits.device
+    G = lwe.shape[0]
+    dev = lwe.device
     kN = p.big_dim
     lc = p.cbs_level
-    weights = [1 << (64 - (lv + 1) * p.cbs_base_log) for lv in range(lc)]
-    rep = bits.repeat_interleave(lc, dim=0)
-    idx = torch.arange(lc, dtype=torch.int32, device=dev).repeat(G)
-    lwe = _sign_bootstrap(ev, rep, weights, idx)                     # [G*lc, kN+1]: bit * 2^(64-(lv+1)*b)
     ext = torch.zeros((G * lc, kN + PF_PAD + 1), dtype=torch.int64, device=dev)
-    ext[:, :kN + 1] = lwe                                            # body -> mask slot kN (key entry -1)
+    ext[:, :kN + 1] = lwe.reshape(G * lc, kN + 1)                    # body -> mask slot kN (key entry -1)
     rows = ev.packing.apply(ext)                                     # [G*lc, (k+1)^2 N] = [G][lv][r][(k+1)N]
     lib = _lib.load()
     out = torch.empty((lib.fhe_bsk_fourier_elems(G, p.k, p.N, lc), 2), dtype=torch.float64, device=dev)
@@ -405,11 +420,11 @@ def wide_table_lookup(ev, cts: Sequence[torch.Tensor], pool: torch.Tensor, polys
                 part = part.clone()
             parts.append(part)
         _tick("start")
-        blist = [b for per_residue in extract_bits_multi(ev, parts, moduli) for b in per_residue]
-        stacked = torch.stack(blist, dim=1).reshape(n_ct * bits, p.n + 1)          # [e][t]
-        _tick("extract")
+        levels = [lv for per_residue in extract_and_bootstrap(ev, parts, moduli)[1] for lv in per_residue]
+        stacked = torch.stack(levels, dim=1).reshape(n_ct * bits, p.cbs_level, p.ct_words)      # [e][t][lv]
+        _tick("extract+bootstrap")
         ggsw_f = circuit_bootstrap(ev, stacked)
-        _tick("circuit_bootstrap")
+        _tick("packing+fourier")
         tsel = torch.zeros(n_ct, dtype=torch.int64, device=stacked.device) if table_idx is None else table_idx[lo:hi].to(torch.int64)
         for o in range(r):
             first = (tsel * r + o) * polys_per_residue

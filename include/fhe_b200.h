@@ -115,6 +115,13 @@ int fhe_pbs_batch_variant(uint64_t* out, const uint64_t* in, long B, const void*
  * (k+1)N words (CMUX tree of vertical packing).
  * fhe_blind_rotate_batch: the bootstrap's blind rotation + sample extraction with one list of n GGSWs per
  * ciphertext (ct_stride double2 elements apart) instead of a bootstrap key. */
+/* fhe_pbs_batch_multi: one blind rotation, `nout` <= 2^theta results on the same input (PBSmanyLUT): the
+ * accumulators interleave the functions (coefficient i belongs to function i mod 2^theta), the modulus switch
+ * keeps theta zero low bits; out [B][nout][kN+1].  Used for the sign bootstraps of bit extraction and circuit
+ * bootstrapping, which all act on the same extracted-bit ciphertext. */
+int fhe_pbs_batch_multi(uint64_t* out, const uint64_t* in, long B, const void* bsk_f, const uint64_t* luts,
+                        const int* lut_idx, int n, int k, int N, int level, int base_log, int theta, int nout,
+                        int variant, void* stream);
 int fhe_cmux_batch(uint64_t* out, const uint64_t* pool, const int* i0, const int* i1, const void* ggsw_f,
                    const int* gi, long B, int k, int N, int level, int base_log,
                    int plain /* pool entries are plaintext polynomials (zero masks) */, void* stream);

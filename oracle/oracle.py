@@ -170,21 +170,22 @@ class Oracle:
                                C.c_int(N), C.c_int(level), C.c_int(base_log))
         return out
 
-    def pbs_ex(self, ct, bsk_f, luts, lut_idx, base_log, n, bsk_ct_stride):
-        """Blind rotation with one list of n Fourier GGSWs per ciphertext (bsk_f: [..., level, k+1, k+1, M, 2];
-        bsk_ct_stride in complex elements)."""
+    def pbs_ex(self, ct, bsk_f, luts, lut_idx, base_log, n, bsk_ct_stride, theta=0, nout=1):
+        """Extended bootstrap.  bsk_ct_stride > 0: one list of n Fourier GGSWs per ciphertext (bsk_f: [..., level,
+        k+1, k+1, M, 2]; stride in complex elements).  theta / nout: multi-output bootstrap, result [B, nout, kN+1]."""
         level, k1, _, M, _ = bsk_f.shape[-5:]
         k, N = k1 - 1, 2 * M
         ct, pc = self._u64(ct)
         luts, pl = self._u64(luts)
         B = ct.size // (n + 1)
-        out = np.empty((B, k * N + 1), dtype=np.uint64)
+        out = np.empty((B, nout, k * N + 1), dtype=np.uint64)
         lut_idx = np.ascontiguousarray(lut_idx, dtype=np.int32)
         bsk_f = np.ascontiguousarray(bsk_f)
         self.lib.ref_pbs_batch_ex(out.ctypes.data_as(_u64p), pc, C.c_long(B), bsk_f.ctypes.data_as(_f64p), pl,
                                   lut_idx.ctypes.data_as(_i32p), C.c_int(n), C.c_int(k), C.c_int(N),
-                                  C.c_int(level), C.c_int(base_log), C.c_long(bsk_ct_stride))
-        return out
+                                  C.c_int(level), C.c_int(base_log), C.c_long(bsk_ct_stride), C.c_int(theta),
+                                  C.c_int(nout))
+        return out[:, 0] if nout == 1 and theta == 0 else out
 
     def cmux_batch(self, pool, i0, i1, ggsw_f, gi, base_log):
         """out[b] = pool[i0[b]] + ggsw[gi[b]] (x) (pool[i1[b]] - pool[i0[b]]); pool [P, (k+1)N]."""

@@ -511,9 +511,18 @@ static void cmux_rotate(const fft_plan *p, u64 *acc, int a, const cplx *ggsw_f, 
 /* bsk_ct_stride: 0 for a bootstrap (one key for the batch); for the blind rotation of the
  * wide-integer lookup every ciphertext brings its own list of n Fourier GGSWs (cplx elements
  * between the lists of consecutive ciphertexts). */
+/* theta / nout: multi-output bootstrap (PBSmanyLUT, Chillotti-Ligier-Orfila-Tap 2021): the modulus switch
+ * keeps theta zero low bits, the accumulator interleaves up to 2^theta functions (coefficient i belongs to
+ * function i mod 2^theta) and coefficients 0..nout-1 are extracted; out is [B][nout][kN+1].  0 / 1 = plain. */
+static inline int modswitch_coarse(u64 x, int log2N, int theta) {
+    int lg = log2N + 1 - theta;
+    u64 t = ((x >> (64 - lg - 1)) + 1) >> 1;
+    return (int)((t & ((1ULL << lg) - 1)) << theta);
+}
+
 void ref_pbs_batch_ex(u64 *out, const u64 *in, long B, const double *bsk_f, const u64 *luts,
                       const int32_t *lut_idx, int n, int k, int N, int level, int base_log,
-                      long bsk_ct_stride) {
+                      long bsk_ct_stride, int theta, int nout) {
     const fft_plan *p = get_plan(N);
     int log2N = 0; while ((1 << log2N) < N) log2N++;
     const int M = N / 2;
@@ -529,23 +538,25 @@ void ref_pbs_batch_ex(u64 *out, const u64 *in, long B, const double *bsk_f, cons
         for (long e = 0; e < B; e++) {
             const u64 *ct = in + (size_t)e * (n + 1);
             const u64 *lut = luts + (size_t)(lut_idx ? lut_idx[e] : 0) * (k + 1) * N;
-            int bt = modswitch(ct[n], log2N);
+            int bt = modswitch_coarse(ct[n], log2N, theta);
             for (int c = 0; c <= k; c++)
                 monomial_mul(acc + (size_t)c * N, lut + (size_t)c * N, (2 * N - bt) % (2 * N), N);
             for (int i = 0; i < n; i++) {
-                int at = modswitch(ct[i], log2N);
+                int at = modswitch_coarse(ct[i], log2N, theta);
                 if (at == 0) continue;
                 cmux_rotate(p, acc, at, (const cplx *)bsk_f + (size_t)e * bsk_ct_stride + (size_t)i * ggsw_c,
                             k, N, level, base_log, tmp, dig, fin, fout);
             }
-            /* sample extract coefficient 0 */
-            u64 *o = out + (size_t)e * ((size_t)k * N + 1);
-            for (int c = 0; c < k; c++) {
-                const u64 *A = acc + (size_t)c * N;
-                o[(size_t)c * N] = A[0];
-                for (int m = 1; m < N; m++) o[(size_t)c * N + m] = (u64)0 - A[N - m];
+            /* sample extract coefficients 0..nout-1: mask word m of polynomial c is A[u-m] (m <= u), -A[N+u-m] */
+            for (int u = 0; u < nout; u++) {
+                u64 *o = out + ((size_t)e * nout + u) * ((size_t)k * N + 1);
+                for (int c = 0; c < k; c++) {
+                    const u64 *A = acc + (size_t)c * N;
+                    for (int m = 0; m <= u; m++) o[(size_t)c * N + m] = A[u - m];
+                    for (int m = u + 1; m < N; m++) o[(size_t)c * N + m] = (u64)0 - A[N + u - m];
+                }
+                o[(size_t)k * N] = acc[(size_t)k * N + u];
             }
-            o[(size_t)k * N] = acc[(size_t)k * N];
         }
         free(acc); free(tmp); free(dig); free(fin); free(fout);
     }
@@ -553,7 +564,7 @@ void ref_pbs_batch_ex(u64 *out, const u64 *in, long B, const double *bsk_f, cons
 
 void ref_pbs_batch(u64 *out, const u64 *in, long B, const double *bsk_f, const u64 *luts,
                    const int32_t *lut_idx, int n, int k, int N, int level, int base_log) {
-    ref_pbs_batch_ex(out, in, B, bsk_f, luts, lut_idx, n, k, N, level, base_log, 0);
+    ref_pbs_batch_ex(out, in, B, bsk_f, luts, lut_idx, n, k, N, level, base_log, 0, 0, 1);
 }
 
 /* Batched CMUX on GLWE ciphertexts (selection tree of the wide-integer lookup, "vertical packing",

@@ -129,54 +129,65 @@ class WopKeys:
 
 # ----------------------------------------------------------------- the lookup ----------
 
-def _const_lut(p: WopParams, value: int) -> np.ndarray:
-    acc = np.zeros((p.k + 1) * p.N, dtype=np.uint64)
-    acc[p.k * p.N:] = U(value % (1 << 64))
-    return acc
+def bootstrap_theta(p: WopParams) -> int:
+    """log2 of the functions one blind rotation evaluates: the extraction weight of a bit and its cbs_level
+    circuit-bootstrap levels (multi-output bootstrap, ref_pbs_batch_ex)."""
+    return max(1, int(1 + p.cbs_level - 1).bit_length())
 
 
-def _sign_pbs(orc: Oracle, keys: WopKeys, small: np.ndarray, weights: Sequence[int], idx) -> np.ndarray:
-    """Sign bootstrap: phase in [0, 1/2) -> 0, [1/2, 1) -> weights[idx[e]] (test polynomial -w/2, then + w/2)."""
+def sign_bootstrap_multi(orc: Oracle, keys: WopKeys, small: np.ndarray, ext_weights: Sequence[int], idx) -> np.ndarray:
+    """One blind rotation per row of `small` (phase in [0, 1/2) = bit 0, [1/2, 1) = bit 1), 1 + cbs_level results
+    [R, 1 + cbs_level, kN+1]: bit * ext_weights[idx[e]] and bit * 2^(64-(lv+1)*cbs_base_log).  Function u has the
+    constant test polynomial -w_u/2 on the coefficients congruent to u mod 2^theta; + w_u/2 afterwards."""
     p = keys.p
-    luts = np.stack([_const_lut(p, -(w >> 1)) for w in weights])
-    out = orc.pbs(small, keys.bsk_f, luts, np.asarray(idx, dtype=np.int32), p.pbs_base_log)
-    half = np.array([(w >> 1) % (1 << 64) for w in weights], dtype=np.uint64)[np.asarray(idx)]
-    out[:, -1] += half
+    theta, nout = bootstrap_theta(p), 1 + p.cbs_level
+    cbs_w = [1 << (64 - (lv + 1) * p.cbs_base_log) for lv in range(p.cbs_level)]
+    luts = np.zeros((len(ext_weights), (p.k + 1) * p.N), dtype=np.uint64)
+    half = np.zeros((len(ext_weights), nout), dtype=np.uint64)
+    for a, w in enumerate(ext_weights):
+        ws = [w] + cbs_w
+        for u, wu in enumerate(ws):
+            luts[a, p.k * p.N + u::1 << theta] = U((-(wu >> 1)) % (1 << 64))
+            half[a, u] = U((wu >> 1) % (1 << 64))
+    idx = np.asarray(idx, dtype=np.int32)
+    out = orc.pbs_ex(small, keys.bsk_f, luts, idx, p.pbs_base_log, p.n, 0, theta, nout)
+    out[:, :, -1] += half[idx]
     return out
 
 
-def extract_bits(orc: Oracle, keys: WopKeys, ct: np.ndarray, m: int) -> List[np.ndarray]:
-    """Bits (LSB first) of the cell index of CRT block ciphertexts `ct` [E, kN+1]: small-key ciphertexts whose phase
-    lies in [0, 1/2) for 0 and [1/2, 1) for 1."""
+def extract_and_bootstrap(orc: Oracle, keys: WopKeys, ct: np.ndarray, m: int):
+    """Bits (LSB first) of the cell index of the residues mod m in `ct` [E, kN+1].  Returns (bits, levels): per bit the
+    small-key ciphertext that was tested (phase in [0, 1/2) = 0) and the cbs_level LWEs bit * 2^(64-(lv+1)*b) under the
+    big key [E, cbs_level, kN+1].  The bit is subtracted from the residue with the result of the SAME blind rotation,
+    so extraction and circuit bootstrapping can never disagree on a residue sitting on a cell boundary."""
     p = keys.p
     b, c64, _, _ = block_layout(m)
     buf = ct.copy()
     buf[:, -1] += U((c64 << (64 - b)) >> 6)
-    bits = []
+    bits, levels = [], []
     for t in range(b):
         sh = buf * U(1 << (b - 1 - t))
         ks = orc.keyswitch(sh, keys.ksk, p.ks_level, p.ks_base_log)
         if t:
             # the already removed lower bits leave the fraction in [0, 2^-t): centre it inside the half torus
             ks[:, -1] += U((1 << 62) - (1 << (62 - t)))
+        got = sign_bootstrap_multi(orc, keys, ks, [1 << (64 - b + t)], np.zeros(len(ks), dtype=np.int32))
         bits.append(ks)
+        levels.append(got[:, 1:])
         if t < b - 1:
-            w = 1 << (64 - b + t)
-            buf = buf - _sign_pbs(orc, keys, ks, [w], np.zeros(len(ks), dtype=np.int32))
-    return bits
+            buf = buf - got[:, 0]
+    return bits, levels
 
 
-def circuit_bootstrap(orc: Oracle, keys: WopKeys, bits: np.ndarray) -> np.ndarray:
-    """bits [G, n+1] -> Fourier GGSWs [G, cbs_level, k+1, k+1, M, 2]."""
+def circuit_bootstrap(orc: Oracle, keys: WopKeys, lwe: np.ndarray) -> np.ndarray:
+    """lwe [G, cbs_level, kN+1] (bit * gadget factor per level) -> Fourier GGSWs [G, cbs_level, k+1, k+1, M, 2]:
+    one packing keyswitch per level turns the LWE into the k+1 GLWE rows of that level."""
     p = keys.p
-    G = bits.shape[0]
+    G = lwe.shape[0]
     kN = p.k * p.N
-    weights = [1 << (64 - (lv + 1) * p.cbs_base_log) for lv in range(p.cbs_level)]
-    rep = np.repeat(bits, p.cbs_level, axis=0)
-    idx = np.tile(np.arange(p.cbs_level, dtype=np.int32), G)
-    lwe = _sign_pbs(orc, keys, rep, weights, idx)                    # [G*lc, kN+1]: bit * 2^(64-(lv+1)*b)
-    ext = np.zeros((lwe.shape[0], kN + PF_PAD + 1), dtype=np.uint64)
-    ext[:, :kN + 1] = lwe                                             # the body becomes mask word kN (key entry -1)
+    flat = lwe.reshape(G * p.cbs_level, kN + 1)
+    ext = np.zeros((flat.shape[0], kN + PF_PAD + 1), dtype=np.uint64)
+    ext[:, :kN + 1] = flat                                            # the body becomes mask word kN (key entry -1)
     rows = orc.keyswitch(ext, keys.pfksk, p.pf_level, p.pf_base_log)  # [G*lc, (k+1)^2 N]
     ggsw = rows.reshape(G, p.cbs_level, p.k + 1, p.k + 1, p.N)
     return orc.bsk_to_fourier(ggsw)
@@ -235,11 +246,11 @@ def wide_lookup(orc: Oracle, keys: WopKeys, cts: List[np.ndarray], moduli: Seque
     """cts: one [E, kN+1] array per CRT block of the inputs; returns one array per output block."""
     moduli_out = list(moduli) if moduli_out is None else list(moduli_out)
     E = cts[0].shape[0]
-    bits = []
+    levels = []
     for ct, m in zip(cts, moduli):
-        bits += extract_bits(orc, keys, ct, m)
-    T = len(bits)
-    stacked = np.stack(bits, axis=1).reshape(E * T, -1)              # [e][t]
+        levels += extract_and_bootstrap(orc, keys, ct, m)[1]
+    T = len(levels)
+    stacked = np.stack(levels, axis=1).reshape(E * T, keys.p.cbs_level, -1)      # [e][t][lv]
     ggsw_f = circuit_bootstrap(orc, keys, stacked)
     lut = build_crt_lut(table, moduli, moduli_out)
     return [vertical_packing(orc, keys, ggsw_f, E, T, lut[o:o + 1]) for o in range(len(moduli_out))]

@@ -49,12 +49,12 @@ def torus_dist(a, b):
     return np.abs(d) / 2.0 ** 64
 
 
-def sign_decision(ct, sk_small, N):
+def sign_decision(ct, sk_small, N, theta):
     """What a sign bootstrap decides for small-key ciphertexts: the half of Z_2N the modulus-switched phase falls in
-    (a residue sitting exactly on a cell boundary may go either way, but every bootstrap of the same ciphertext goes
-    the same way, and both neighbouring cells decode to that residue)."""
-    lg = N.bit_length()          # log2(2N)
-    ms = (((ct >> np.uint64(64 - lg - 1)) + np.uint64(1)) >> np.uint64(1)) & np.uint64(2 * N - 1)
+    (a residue sitting exactly on a cell boundary may go either way, but both neighbouring cells decode to that
+    residue).  The multi-output bootstrap switches to multiples of 2^theta."""
+    lg = N.bit_length() - theta          # log2(2N) - theta
+    ms = ((((ct >> np.uint64(64 - lg - 1)) + np.uint64(1)) >> np.uint64(1)) & np.uint64((1 << lg) - 1)) << np.uint64(theta)
     ph = (ms[:, -1].astype(np.int64) - (ms[:, :-1].astype(np.int64) * sk_small.astype(np.int64)[None, :]).sum(axis=1)) % (2 * N)
     return (ph >= N).astype(np.int64)
 
@@ -88,14 +88,24 @@ def test_extract_bits_decisions(oracle, setup, cuda_device):
     cts = encrypt_residues(oracle, keys, p, x)
     for ct, m in zip(cts, p.moduli):
         b, off, dec, _ = wide.block_layout(m)
-        bits = wide.extract_bits(ev, E.from_np_u64(ct, cuda_device), m)
-        ref_bits = W.extract_bits(oracle, keys, ct, m)
-        assert len(bits) == b
+        bits, levels = wide.extract_and_bootstrap(ev, [E.from_np_u64(ct, cuda_device)], [m])
+        bits, levels = bits[0], levels[0]
+        ref_bits, ref_levels = W.extract_and_bootstrap(oracle, keys, ct, m)
+        assert len(bits) == b and len(levels) == b
+        theta = wide.bootstrap_theta(p)
+        assert theta == W.bootstrap_theta(keys.p)
         cell = np.zeros(len(x), dtype=np.int64)
         for t, (g, r) in enumerate(zip(bits, ref_bits)):
-            d, d_ref = sign_decision(E.to_np_u64(g), keys.sk_small, p.N), sign_decision(r, keys.sk_small, p.N)
+            d, d_ref = sign_decision(E.to_np_u64(g), keys.sk_small, p.N, theta), sign_decision(r, keys.sk_small, p.N, theta)
             assert np.array_equal(d, d_ref)
             cell |= d << t
+            # the circuit-bootstrap inputs of this bit: bit * 2^(64-(lv+1)*b) under the big key, from the same rotation
+            lv_gpu = E.to_np_u64(levels[t].contiguous())
+            for lv in range(p.cbs_level):
+                want = d.astype(np.uint64) << np.uint64(64 - (lv + 1) * p.cbs_base_log)
+                ph = oracle.decrypt_phase(lv_gpu[:, lv], keys.sk_big)
+                ph_ref = oracle.decrypt_phase(ref_levels[t][:, lv], keys.sk_big)
+                assert torus_dist(ph, want).max() < 2.0 ** -24 and torus_dist(ph_ref, want).max() < 2.0 ** -24
         assert np.array_equal(np.asarray(dec)[cell], x % m)
 
 
@@ -105,8 +115,10 @@ def test_cmux_batch_matches_oracle(oracle, setup, cuda_device):
     G = 6
     bitvals = rng.integers(0, 2, G)
     small = oracle.encrypt((bitvals.astype(np.uint64) << np.uint64(63)) + np.uint64(1 << 62), keys.sk_small, p.lwe_std, 901)
-    ggsw_ref = W.circuit_bootstrap(oracle, keys, small)
-    ggsw = wide.circuit_bootstrap(ev, E.from_np_u64(small, cuda_device))
+    zero_idx = np.zeros(G, dtype=np.int32)
+    ggsw_ref = W.circuit_bootstrap(oracle, keys, W.sign_bootstrap_multi(oracle, keys, small, [1 << 60], zero_idx)[:, 1:])
+    ggsw = wide.circuit_bootstrap(ev, wide.sign_bootstrap_multi(ev, E.from_np_u64(small, cuda_device), [1 << 60],
+                                                                torch.from_numpy(zero_idx).to(cuda_device))[:, 1:].contiguous())
     glwe = (p.k + 1) * p.N
     pool = np.zeros((8, glwe), dtype=np.uint64)
     pool[:, p.k * p.N:] = rng.integers(0, 1 << 63, (8, p.N), dtype=np.int64).astype(np.uint64) << np.uint64(1)
