@@ -167,8 +167,11 @@ def run_ours(args):
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner there at every debug level the box may
+        # preset (VERSION / WARN); send its diagnostics to stderr's neighbour instead unless the user asked for a file
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_bench_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     doc = golden()

@@ -344,7 +344,18 @@ def wide():
          [np.array([0, 600, 429]), rng.integers(0, 601, (3,))])
 
 
-GROUPS = {"wide": wide, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "ops": ops, "ka": known_answers,
+def cfg3b():
+    """BASELINE config 3, variant (B) of SURVEY 8d: dense 6-bit x, ternary W -> 13-bit accumulators, i.e. the circuit
+    the reference's compiler would run on its CRT / without-padding path."""
+    wr = np.random.default_rng(1)
+    W = ternary_weights(wr, (128, 64), 40, 128)
+    data = np.random.default_rng(0)
+    inputset = [data.integers(0, 64, (64, 128)) for _ in range(20)] + [np.zeros((64, 128), dtype=np.int64), np.full((64, 128), 63)]
+    emit("cfg3b_matmul6_dense_relu", lambda x: np.maximum(x @ W, 0), {"x": "encrypted"}, inputset,
+         [data.integers(0, 64, (64, 128))])
+
+
+GROUPS = {"cfg3b": cfg3b, "wide": wide, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "ops": ops, "ka": known_answers,
           "cfg5small": lambda: cfg5(8)}
 
 if __name__ == "__main__":

@@ -17,7 +17,7 @@ import torch
 from concrete_numpy_b200 import api
 from golden_util import load_golden, same, to_value
 
-NAMES = ["cfg1_lut4_1024", "cfg2_univariate8_64x64", "cfg3_matmul6_relu", "cfg4_conv2d_relu",
+NAMES = ["cfg1_lut4_1024", "cfg2_univariate8_64x64", "cfg3_matmul6_relu", "cfg3b_matmul6_dense_relu", "cfg4_conv2d_relu",
          "cfg5_kvdb128_query", "cfg5_kvdb128_replace", "cfg5_kvdb128_insert"]
 only = sys.argv[1:]
 res = {}
@@ -51,7 +51,7 @@ for name in NAMES:
     p = circuit.server.client_specs.client_parameters.crypto
     res[name] = {"ok": bool(ok), "latency_ms": round(ms, 3), "n_pbs": int(fb.n_pbs), "pbs_per_s": round(fb.n_pbs / (ms * 1e-3), 1),
                  "params": {"p": p.p, "n": p.n, "k": p.k, "N": p.N, "pbs_level": p.pbs_level, "pbs_base_log": p.pbs_base_log,
-                            "ks_level": p.ks_level, "ks_base_log": p.ks_base_log},
+                            "ks_level": p.ks_level, "ks_base_log": p.ks_base_log, "moduli": list(p.moduli)},
                  "setup_s": round(t_setup, 2)}
     print(name, json.dumps(res[name]), flush=True)
     circuit.cleanup()

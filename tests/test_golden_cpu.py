@@ -64,7 +64,7 @@ def test_pbs_counts_match_survey(clear_backend):
         assert (info.n_pbs, info.tlu_depth, info.precision) == (n_pbs, depth, p), name
 
 
-WIDE = golden_names("wide_")
+WIDE = golden_names("wide_") + ["cfg3b_matmul6_dense_relu"]
 
 
 @pytest.mark.parametrize("name", WIDE)

@@ -20,7 +20,7 @@ FAST = [n for n in golden_names() if n.startswith(("ops_", "ka_", "cfg5_kvdb8", 
 HEAVY = [n for n in golden_names() if n.startswith(("cfg2", "cfg4", "cfg5_kvdb128"))]
 
 
-WIDE = [n for n in golden_names() if n.startswith("wide_")]      # 9..16-bit circuits: CRT residues + wide lookup
+WIDE = [n for n in golden_names() if n.startswith("wide_")]      # (cfg3b, 11 bits at full size, runs with FAST)      # 9..16-bit circuits: CRT residues + wide lookup
 
 
 def check(name):
