@@ -678,7 +678,48 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
             mid_passes<P, false>(work, J, tw);
             PBS_PROF(2)
             // ---- P3: last forward pass + multiply-accumulate against GGSW_i + first inverse pass
-            {
+            if constexpr ((NG < NT) && (NT % NG == 0) && (P::KMAX + 1 <= NT / NG)) {
+                // fewer butterfly groups than threads (N = 2048 with 256 threads): the thread groups split the k+1
+                // outputs between them -- each thread transforms its inputs and accumulates ONE output polynomial
+                // (half the GGSW loads and FMAs per thread instead of half the threads idle)
+                const double2* gg = bskF + (size_t)i * ggsw_stride;
+                const int w = tid % NG, o = tid / NG;
+                const bool act = o <= k;
+                const size_t o_stride = (size_t)P::C << P::LOGBUF;
+                const double2* gp = gg + ((size_t)rank << P::LOGBUF) + w + (act ? o : 0) * o_stride;
+                double2 r[RF], gv[RF];
+#pragma unroll
+                for (int m = 0; m < RF; m++) {
+                    r[m] = make_double2(0.0, 0.0);
+                    gv[m] = __ldg(gp + m * NG);
+                }
+#pragma unroll 1
+                for (int j = 0; j < J; j++) {
+                    double2 x[RF];
+                    const double2* base = work + ((size_t)j << P::LOGBUF);
+#pragma unroll
+                    for (int m = 0; m < RF; m++) x[m] = base[SW(w * RF + m)];
+                    Dft<RF, false>::run(x);
+                    const double2* gn = gp + (size_t)(j + 1) * (k + 1) * o_stride;
+                    const bool more = (j + 1 < J);
+#pragma unroll
+                    for (int m = 0; m < RF; m++) {
+                        const double2 b = gv[m];
+                        r[m].x = fma(x[m].x, b.x, r[m].x);
+                        r[m].x = fma(-x[m].y, b.y, r[m].x);
+                        r[m].y = fma(x[m].x, b.y, r[m].y);
+                        r[m].y = fma(x[m].y, b.x, r[m].y);
+                        if (more) gv[m] = __ldg(gn + m * NG);
+                    }
+                }
+                __syncthreads();      // the other groups still read the buffers the outputs overwrite
+                if (act) {
+                    Dft<RF, true>::run(r);
+                    double2* base = work + ((size_t)o << P::LOGBUF);
+#pragma unroll
+                    for (int m = 0; m < RF; m++) base[SW(w * RF + m)] = r[m];
+                }
+            } else {
                 const double2* gg = bskF + (size_t)i * ggsw_stride;
 #pragma unroll 1
                 for (int w = tid; w < NG; w += NT) {

@@ -7,10 +7,13 @@ from concrete_numpy_b200.params import REFERENCE_SETS
 
 dev = torch.device("cuda:0")
 NAMES = ["P1 decomp+stage1", "sync A", "mid fwd", "fused MAC", "mid inv", "sync B", "P5 gather+acc", "sync C", "extract+init"]
-for pbits, B in ((8, 36), (6, 148), (4, 888)):
-    p = REFERENCE_SETS[pbits]
+# "w" = the bootstrap of the 16-bit wide lookup (N = 2048, 3 levels, 256-thread plan), run as a 4-bit bootstrap
+WIDE_PBS = E.CryptoParams(p=4, n=644, k=1, N=2048, pbs_level=3, pbs_base_log=11, ks_level=4, ks_base_log=3,
+                          lwe_std=2.0 ** -14.5, glwe_std=2.0 ** -51.6)
+for pbits, B in ((8, 36), (6, 148), (4, 888), ("w", 444)):
     if len(sys.argv) > 1 and str(pbits) not in sys.argv[1:]:
         continue
+    p = WIDE_PBS if pbits == "w" else REFERENCE_SETS[pbits]
     ks = E.KeySet(p, dev, seed=1)
     ev = E.EvalKeys.of(ks)
     rng = np.random.default_rng(0)
