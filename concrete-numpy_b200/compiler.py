@@ -138,7 +138,9 @@ class CompilationFeedback:
         self.total_secret_keys_size = int(8 * (crypto.n + crypto.big_dim))
         self.total_bootstrap_keys_size = int(8 * crypto.n * crypto.pbs_level * (crypto.k + 1) ** 2 * crypto.N)
         self.total_keyswitch_keys_size = int(8 * crypto.big_dim * crypto.ks_level * (crypto.n + 1))
-        if crypto.wide:
+        if crypto.linear_only:
+            self.complexity = float(sum(t.size for t in program.result_types) * crypto.ct_words)
+        elif crypto.wide:
             from . import wide
 
             self.complexity = float(info.n_pbs * P.wide_lookup_flops(crypto))
@@ -229,7 +231,7 @@ def _compile(mlir: str, options: CompilationOptions, cls):
             raise RuntimeError(f"pinned parameters carry {crypto.p} bits, circuit needs {info.precision}")
         if crypto.wide:
             info = analyze(program, crypto.moduli)
-        elif wide_mode:
+        elif wide_mode and info.n_pbs > 0:
             raise RuntimeError(f"{info.precision}-bit circuits need CRT parameters (moduli)")
     else:
         n = max(info.n_pbs, 1)
@@ -242,7 +244,10 @@ def _compile(mlir: str, options: CompilationOptions, cls):
         norm2_q = float(2 ** math.ceil(math.log2(max(info.norm2, 1.0))))
         target_q = float(10.0 ** math.floor(math.log10(target) + 1e-9))
         try:
-            if wide_mode:
+            if info.n_pbs == 0:
+                # no table lookup: any width that fits a torus word, no evaluation keys (graph_converter.py:288-306)
+                crypto = P.select_linear_parameters(info.precision, norm2_q, target_q)
+            elif wide_mode:
                 from . import wide
 
                 if info.precision > 16:
@@ -254,7 +259,14 @@ def _compile(mlir: str, options: CompilationOptions, cls):
                 crypto = P.select_parameters(info.precision, norm2_q, target_q)
         except ValueError as error:
             raise RuntimeError(f"Unfeasible parameter search: {error}") from error
-    p_err = P.estimate_wide_p_error(crypto, info.norm2) if crypto.wide else P.estimate_p_error(crypto, info.norm2)
+    if crypto.wide:
+        p_err = P.estimate_wide_p_error(crypto, info.norm2)
+    elif crypto.linear_only:
+        if info.n_pbs:
+            raise RuntimeError("parameters without bootstrap keys cannot run a circuit with table lookups")
+        p_err = P.p_error_of(crypto.p, max(info.norm2, 1.0) * crypto.glwe_std ** 2)
+    else:
+        p_err = P.estimate_p_error(crypto, info.norm2)
     if options.display_optimizer_choice:
         print(f"--- Circuit\n  {info.precision} bits integers\n  {info.norm2:g} manp (squared 2-norm)\n"
               f"  {info.n_pbs} table lookups, depth {info.tlu_depth}\n--- Optimizer choice\n  {crypto}\n"

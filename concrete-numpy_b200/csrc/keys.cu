@@ -229,7 +229,7 @@ int fhe_trivial_lwe_batch(u64* ct, const u64* plaintexts, long B, int dim, void*
 // phase and/or msg may be null; msg is decoded at precision p (one padding bit)
 int fhe_decrypt_lwe_batch(u64* phase, u64* msg, const u64* ct, long B, const u64* sk, int dim, int p,
                           void* stream) {
-    if (B < 0 || dim <= 0 || (msg && (p < 1 || p > 16))) FHE_FAIL(2, "decrypt_lwe_batch: bad arguments");
+    if (B < 0 || dim <= 0 || (msg && (p < 1 || p > 60))) FHE_FAIL(2, "decrypt_lwe_batch: bad arguments");
     if (B == 0) return 0;
     k_decrypt<<<(unsigned)B, 128, 0, (cudaStream_t)stream>>>(phase, msg, ct, sk, dim, p);
     FHE_CHECK_LAUNCH();

@@ -50,6 +50,11 @@ class CryptoParams:
         return len(self.moduli) > 0
 
     @property
+    def linear_only(self) -> bool:
+        """Circuits without table lookups carry no bootstrap / keyswitch keys (params.select_linear_parameters)."""
+        return self.pbs_level == 0
+
+    @property
     def big_dim(self) -> int:
         return self.k * self.N
 
@@ -89,10 +94,18 @@ class KeySet:
         dev = self.device
         with torch.cuda.device(dev):
             st = _stream()
-            self.sk_small = torch.empty(p.n, dtype=torch.int64, device=dev)
             self.sk_big = torch.empty(p.big_dim, dtype=torch.int64, device=dev)
-            _lib.call("fhe_keygen_lwe_secret", self.sk_small.data_ptr(), p.n, self.seed, DOM_SK_SMALL, st)
             _lib.call("fhe_keygen_lwe_secret", self.sk_big.data_ptr(), p.big_dim, self.seed, DOM_SK_BIG, st)
+            if p.linear_only:           # no table lookups: nothing to bootstrap or keyswitch with
+                self.sk_small = torch.empty(0, dtype=torch.int64, device=dev)
+                self.ksk = torch.empty((0, 0, 1), dtype=torch.int64, device=dev)
+                self.bsk_std = None
+                self.bsk_f = torch.empty((0, 2), dtype=torch.float64, device=dev)
+                self.pfksk = None
+                torch.cuda.current_stream().synchronize()
+                return
+            self.sk_small = torch.empty(p.n, dtype=torch.int64, device=dev)
+            _lib.call("fhe_keygen_lwe_secret", self.sk_small.data_ptr(), p.n, self.seed, DOM_SK_SMALL, st)
             self.ksk = torch.empty((p.big_dim, p.ks_level, p.n + 1), dtype=torch.int64, device=dev)
             _lib.call("fhe_keygen_ksk", self.ksk.data_ptr(), self.sk_big.data_ptr(), p.big_dim,
                       self.sk_small.data_ptr(), p.n, p.ks_level, p.ks_base_log, p.lwe_std, self.seed, st)
@@ -158,12 +171,13 @@ class EvalKeys:
             self.packing = wide.PackingKey(params, pfksk)
         self._variants = {0: bsk_f}
         lib = _lib.load()
-        n = lib.fhe_pbs_num_variants(params.N, params.k, params.pbs_level)
+        n = 0 if params.linear_only else lib.fhe_pbs_num_variants(params.N, params.k, params.pbs_level)
         self.variant_clusters = [lib.fhe_pbs_variant_cluster_size(params.N, params.k, params.pbs_level, v)
                                  for v in range(max(n, 0))]
         self._capacity = None      # ciphertexts each variant bootstraps in one wave (queried on the device)
         # tensor-core keyswitch (csrc/keyswitch_tc.cu): key bytes re-laid out once, on first use
-        self.ks_tc_ok = bool(lib.fhe_ks_tc_supported(params.big_dim, params.n, params.ks_level, params.ks_base_log))
+        self.ks_tc_ok = (not params.linear_only) and bool(
+            lib.fhe_ks_tc_supported(params.big_dim, params.n, params.ks_level, params.ks_base_log))
         self._ksk_tc = None
 
     def ksk_tc(self) -> torch.Tensor:

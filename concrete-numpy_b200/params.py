@@ -183,6 +183,29 @@ def select_parameters(p: int, norm2: float = 1.0, p_error: float = 1e-9) -> Cryp
                         glwe_std=2.0 ** secure_log2_std(k * N))
 
 
+# ---------------------------------------------------------------- circuits without table lookups ----
+
+MAX_LINEAR_BITS = 55
+
+
+@lru_cache(maxsize=None)
+def select_linear_parameters(p: int, norm2: float = 1.0, p_error: float = 1e-9) -> CryptoParams:
+    """Parameters of a circuit WITHOUT table lookups (the reference accepts any width there, only lookups are limited
+    to 16 bits: concrete/numpy/mlir/graph_converter.py:288-306, e.g. tests/execution/test_add.py with values up to
+    10^6): one LWE ciphertext per value in the native encoding, no bootstrap / keyswitch keys at all.  The LWE
+    dimension is the smallest whose 128-bit-secure noise leaves the half-step 2^-(p+2) at the requested error rate."""
+    if p < 1 or p > MAX_LINEAR_BITS:
+        raise ValueError(f"{p}-bit values do not fit one 64-bit torus ciphertext (up to {MAX_LINEAR_BITS} bits)")
+    z = _z_for_p_error(p_error)
+    need = -(p + 2) - math.log2(z) - 0.5 * math.log2(max(norm2, 1.0))       # log2 of the largest admissible noise std
+    if need < MIN_LOG2_STD:
+        raise ValueError(f"no noise level supports {p} bits with 2-norm^2={norm2:g} at p_error={p_error:g}")
+    dim = int(math.ceil((need - SECURITY_BIAS) / SECURITY_SLOPE))
+    dim = max(512, (dim + 15) // 16 * 16)
+    return CryptoParams(p=p, n=0, k=1, N=dim, pbs_level=0, pbs_base_log=0, ks_level=0, ks_base_log=0,
+                        lwe_std=0.0, glwe_std=2.0 ** secure_log2_std(dim))
+
+
 # ---------------------------------------------------------------- wide integers (CRT) ----
 
 def variance_packing_keyswitch(kN, level, base_log, glwe_var):

@@ -355,7 +355,30 @@ def cfg3b():
          [data.integers(0, 64, (64, 128))])
 
 
-GROUPS = {"cfg3b": cfg3b, "wide": wide, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "ops": ops, "ka": known_answers,
+def linear_wide():
+    """Circuits without table lookups at widths beyond 16 bits (graph_converter.py:288-306 only limits circuits WITH
+    lookups); value ranges of tests/execution/test_add.py:62-68 ([0, 1000000])."""
+    rng = np.random.default_rng(11)
+
+    def ins(lo, hi, shape, n=10):
+        return [rng.integers(lo, hi + 1, shape) for _ in range(n)] + [np.full(shape, lo, dtype=np.int64), np.full(shape, hi, dtype=np.int64)]
+
+    emit("lin_add_const_20bit", lambda x: x + 42, {"x": "encrypted"}, ins(0, 1000000, (3,)),
+         [np.array([0, 1000000, 123456]), rng.integers(0, 1000001, (3,))])
+    emit("lin_mul_sub_31bit", lambda x, y: x * 1000 - y, {"x": "encrypted", "y": "encrypted"},
+         list(zip(ins(0, 1000000, (2, 2)), ins(0, 1000000, (2, 2))))
+         + [(np.zeros((2, 2), dtype=np.int64), np.full((2, 2), 1000000)), (np.full((2, 2), 1000000), np.zeros((2, 2), dtype=np.int64))],
+         [(np.array([[0, 1000000], [1, 999999]]), np.array([[1000000, 0], [1000000, 7]])),
+          (rng.integers(0, 1000001, (2, 2)), rng.integers(0, 1000001, (2, 2)))])
+    W = np.array([[5000, -7], [3, 2500], [-4100, 9]], dtype=np.int64)
+    corner = [np.array([[1000, 1000, 0], [0, 0, 1000]]), np.array([[0, 1000, 0], [1000, 0, 1000]])]   # extreme sums
+    emit("lin_matmul_24bit", lambda x: x @ W, {"x": "encrypted"}, ins(0, 1000, (2, 3)) + corner,
+         [corner[0], rng.integers(0, 1001, (2, 3))])
+    emit("lin_sum_neg_31bit", lambda x: -np.sum(x * 1003), {"x": "encrypted"}, ins(0, 100000, (8,)),
+         [np.full((8,), 100000), rng.integers(0, 100001, (8,))])
+
+
+GROUPS = {"lin": linear_wide, "cfg3b": cfg3b, "wide": wide, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "ops": ops, "ka": known_answers,
           "cfg5small": lambda: cfg5(8)}
 
 if __name__ == "__main__":

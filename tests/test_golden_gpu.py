@@ -16,7 +16,7 @@ from golden_util import golden_names, load_golden, same, to_value
 
 os.environ.setdefault("CNP_B200_KEY_SEED", "20261019")
 
-FAST = [n for n in golden_names() if n.startswith(("ops_", "ka_", "cfg5_kvdb8", "cfg1", "cfg3"))]
+FAST = [n for n in golden_names() if n.startswith(("ops_", "ka_", "lin_", "cfg5_kvdb8", "cfg1", "cfg3"))]
 HEAVY = [n for n in golden_names() if n.startswith(("cfg2", "cfg4", "cfg5_kvdb128"))]
 
 

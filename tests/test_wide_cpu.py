@@ -94,6 +94,9 @@ def test_wide_circuits_compile_with_crt_client_parameters():
         opt = cc.CompilationOptions.new("main")
         opt.set_global_p_error(doc["global_p_error"])
         res = cc.JITSupport.new().compile(doc["mlir"], opt)
+        if res.info.n_pbs == 0:          # no table lookup: one ciphertext per value, no evaluation keys
+            assert res.crypto.linear_only and not res.crypto.wide
+            continue
         assert res.crypto.wide and 9 <= res.crypto.p <= 16
         cp = json.loads(res.client_parameters.serialize())
         for gate in cp["inputs"] + cp["outputs"]:
@@ -111,3 +114,18 @@ def test_analysis_reduces_weights_per_modulus():
     for m in (5, 7, 11, 13, 16):
         r = _centered(c, m)
         assert np.all((r - c) % m == 0) and r.min() >= -(m // 2) - (m % 2 == 0) * 0 and r.max() <= m // 2
+
+
+def test_linear_only_circuits_take_any_width():
+    """Circuits without table lookups are not limited to 16 bits in the reference (graph_converter.py:288-306;
+    tests/execution/test_add.py runs x + 42 with x up to 10^6): one ciphertext per value, no bootstrap keys."""
+    from concrete_numpy_b200 import params as P
+
+    for p, norm2 in [(4, 1.0), (20, 1.0), (32, 100.0), (50, 1.0)]:
+        prm = P.select_linear_parameters(p, norm2, 1e-9)
+        assert prm.linear_only and not prm.wide and prm.n == 0 and prm.N % 16 == 0
+        assert P.p_error_of(p, norm2 * prm.glwe_std ** 2) <= 1e-9
+        assert abs(np.log2(prm.glwe_std) - P.secure_log2_std(prm.N)) < 1e-9
+    assert P.select_linear_parameters(20).N < P.select_linear_parameters(40).N
+    with pytest.raises(ValueError):
+        P.select_linear_parameters(60)
