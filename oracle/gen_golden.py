@@ -304,6 +304,15 @@ def ops():
     case("two_outputs_style", lambda x, y: (x + y) * 2 - y, {"x": (E, 0, 9, (2,)), "y": (E, 0, 9, (2,))})
     case("unused_arg", lambda x, y: x + 10, {"x": (E, 0, 10, ()), "y": (E, 0, 1, ())})
 
+    # iteration over an encrypted tensor (test_iter.py)
+    def iter_sum(x):
+        result = cnp.zeros(x.shape[1:])
+        for value in x:
+            result += value
+        return result
+
+    case("iter_sum", iter_sum, {"x": (E, 0, 3, (3, 2, 4))})
+
 
 def known_answers():
     """Known-answer circuits of the reference (tests/compilation/test_circuit.py:132-192, 307-345;
