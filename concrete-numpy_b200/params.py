@@ -260,7 +260,7 @@ def estimate_wide_p_error(params: CryptoParams, norm2: float) -> float:
 
 def wide_lookup_flops(params: CryptoParams) -> float:
     """fp64-equivalent work of one wide lookup (all residues)."""
-    from .wide import PF_PAD, block_bits, total_bits
+    from .wide import PF_PAD, total_bits
 
     T = total_bits(params.moduli)
     n_boot = T                     # one multi-output bootstrap per extracted bit

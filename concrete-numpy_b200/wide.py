@@ -24,6 +24,7 @@ algorithm on top of the C ABI:
 PyTorch only allocates buffers and moves rows; every ciphertext operation is a C-ABI call.
 """
 
+import os
 from functools import lru_cache
 from typing import List, Optional, Sequence, Tuple
 
@@ -194,8 +195,6 @@ class PackingKey:
 
     def apply(self, lwe_ext: torch.Tensor) -> torch.Tensor:
         """lwe_ext [B, kin + 1] (body moved to mask slot kN, last word 0) -> [B, (k+1)^2 N] GGSW level rows."""
-        import os
-
         p = self.params
         B = lwe_ext.shape[0]
         out = torch.empty((B, self.nout + 1), dtype=torch.int64, device=lwe_ext.device)
@@ -221,14 +220,6 @@ class PackingKey:
 def _i64(v: int) -> int:
     v &= (1 << 64) - 1
     return v - (1 << 64) if v >= (1 << 63) else v
-
-
-def _const_accumulators(params, values: Sequence[int], device) -> torch.Tensor:
-    """[len(values), (k+1)N] trivial GLWE accumulators with constant body polynomials."""
-    acc = np.zeros((len(values), (params.k + 1) * params.N), dtype=np.uint64)
-    for i, v in enumerate(values):
-        acc[i, params.k * params.N:] = np.uint64(v % (1 << 64))
-    return E.from_np_u64(acc, device)
 
 
 def bootstrap_theta(params) -> int:
