@@ -127,6 +127,11 @@ def ks_macs(kN, n, level):
 
 KS_MAC_COST = 7.0   # one u64 MAC on the int pipe costs about this many fp64 flops of device time
 
+WIDE_SHAPES = ((1, 2048), (1, 4096), (2, 1024), (3, 512))      # (k, N) candidates of the wide search
+# fraction of the k = 1, N = 2048 kernels' flop rate the bootstrap reaches at each shape (16-bit lookups on B200,
+# scripts/wide_bench.py: 7.0 / 3.5 / 2.5 TFLOP/s; profiles/r01_wide_lookup_bench.log): the search minimises time
+WIDE_SHAPE_EFFICIENCY = {(1, 2048): 1.0, (1, 4096): 0.9, (2, 1024): 0.5, (3, 512): 0.36}
+
 
 @lru_cache(maxsize=None)
 def select_parameters(p: int, norm2: float = 1.0, p_error: float = 1e-9) -> CryptoParams:
@@ -171,7 +176,8 @@ def select_parameters(p: int, norm2: float = 1.0, p_error: float = 1e-9) -> Cryp
                         if not np.any(ok):
                             continue
                         cost = pbs_cost + KS_MAC_COST * k * N * ks_level * (n_grid + 1)
-                        cost = np.where(ok, cost, np.inf)
+                        # modelled work -> time: the k > 1 plans reach a fraction of the k = 1 kernels' flop rate
+                        cost = np.where(ok, cost, np.inf) / WIDE_SHAPE_EFFICIENCY.get((k, N), 1.0)
                         j = int(np.argmin(cost))
                         if best is None or cost[j] < best[0]:
                             best = (float(cost[j]), int(n_grid[j]), k, N, level, base_log, ks_level, ks_base_log)
@@ -273,12 +279,6 @@ def wide_lookup_flops(params: CryptoParams) -> float:
     wide_state = 1.15 if params.pbs_level * params.pbs_base_log > 30 else 1.0
     return (n_boot * wide_state * pbs_flops(params.n, params.k, params.N, params.pbs_level)
             + T * KS_MAC_COST * ks_macs(params.big_dim, params.n, params.ks_level) + packing + vp)
-
-
-WIDE_SHAPES = ((1, 2048), (1, 4096), (2, 1024), (3, 512))      # (k, N) candidates of the wide search
-# fraction of the k = 1, N = 2048 kernels' flop rate the bootstrap reaches at each shape (16-bit lookups on B200,
-# scripts/wide_bench.py: 7.0 / 3.5 / 2.5 TFLOP/s; profiles/r01_wide_lookup_bench.log): the search minimises time
-WIDE_SHAPE_EFFICIENCY = {(1, 2048): 1.0, (1, 4096): 0.9, (2, 1024): 0.5, (3, 512): 0.36}
 
 
 @lru_cache(maxsize=None)
