@@ -197,3 +197,24 @@ def test_wide_lookup_decrypts_to_table(oracle, setup, cuda_device, mapped):
         outs_ref = W.wide_lookup(oracle, keys, cts, list(p.moduli), tables[0])
         res_ref = [W.decode_residue(oracle.decrypt_phase(o, keys.sk_big), m) for o, m in zip(outs_ref, p.moduli)]
         assert np.array_equal(W.crt_combine(res_ref, p.moduli), want)
+
+
+def test_evaluation_keys_roundtrip_with_packing_key(setup, cuda_device):
+    """EvaluationKeys.serialize / unserialize (reference tests/compilation/test_circuit.py:174-177) carries the packing
+    keyswitch key of the wide path; the restored keys run a lookup."""
+    from concrete_numpy_b200 import compiler as cc
+
+    p, ks, ev, keys = setup
+    blob = cc.EvaluationKeys(p, ks.bsk_f, ks.ksk, ks.pfksk).serialize()
+    back = cc.EvaluationKeys.unserialize(blob, device=cuda_device)
+    assert back.crypto == p and back.crypto.moduli == MODULI
+    assert torch.equal(back.pfksk, ks.pfksk) and torch.equal(back.ksk, ks.ksk) and torch.equal(back.bsk_f, ks.bsk_f)
+    ev2 = back.on(cuda_device)
+    x = np.array([0, 5, 4095, 1234])
+    table = (np.arange(1 << p.p) * 7 + 1) % 4093
+    luts = wide.build_crt_luts(table, p.moduli)
+    pool = wide.lut_pool(p, luts, cuda_device)
+    cts = [E.encrypt_plaintexts(ks, wide.encode_residue(x, m), first_index=100 * i) for i, m in enumerate(p.moduli)]
+    outs = wide.wide_table_lookup(ev2, cts, pool, max(luts.shape[2] // p.N, 1))
+    res = [wide.decode_residue(E.decrypt(ks, o, return_phase=True)[1], m) for o, m in zip(outs, p.moduli)]
+    assert np.array_equal(wide.crt_combine(res, p.moduli), table[x])
