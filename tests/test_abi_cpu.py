@@ -78,3 +78,33 @@ def test_oracle_table_lookup_end_to_end(oracle):
     out = oracle.pbs(oracle.keyswitch(ct, ksk, lk, bk), oracle.bsk_to_fourier(bsk), lut, None, bb)
     got = oracle.decode(oracle.decrypt_phase(out, sk_b), p)
     assert np.array_equal(got, table[m.astype(np.int64)].astype(np.uint64))
+
+
+def test_plan_selection_and_python_mirror():
+    """fhe_pbs_variant_plan (pure host logic, no GPU needed): variant 0 is the smallest cluster that fits, N = 2048
+    with >= 3 levels takes the 256-thread plan, and params.pbs_cluster_size mirrors the cluster size for every shape."""
+    import ctypes as C
+
+    from concrete_numpy_b200 import _lib, params as P
+
+    lib = _lib.load()
+
+    def plan(N, k, level, v=0):
+        m = (C.c_int * 8)()
+        assert lib.fhe_pbs_variant_plan(N, k, level, v, m) == 0
+        return tuple(m)
+
+    assert plan(2048, 1, 1)[5] == 128 and plan(2048, 1, 2)[5] == 128          # two 128-thread CTAs per SM
+    assert plan(2048, 1, 3)[5] == 256 and plan(2048, 1, 4)[5] == 256          # one CTA per SM by shared memory
+    assert plan(32768, 1, 2)[0] == 8 and plan(32768, 1, 3)[0] == 16
+    for logN in range(8, 16):
+        for k in (1, 2, 3):
+            for level in (1, 2, 3, 4):
+                nv = lib.fhe_pbs_num_variants(1 << logN, k, level)
+                c = lib.fhe_pbs_cluster_size(1 << logN, k, level)
+                assert P.pbs_cluster_size(1 << logN, k, level) == c
+                assert (nv == 0) == (c < 0)
+                if nv:
+                    sizes = [lib.fhe_pbs_variant_cluster_size(1 << logN, k, level, v) for v in range(nv)]
+                    assert sizes == sorted(sizes) and sizes[0] == c == plan(1 << logN, k, level)[0]
+    assert lib.fhe_pbs_variant_plan(2048, 1, 1, 99, (C.c_int * 8)()) != 0
