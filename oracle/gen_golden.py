@@ -313,6 +313,18 @@ def ops():
 
     case("iter_sum", iter_sum, {"x": (E, 0, 3, (3, 2, 4))})
 
+    # more univariate / constant-operand cases of test_others.py:125-470
+    case("others_const_floordiv", lambda x: 127 // x, {"x": (E, 1, 127, (3,))})
+    case("others_pow2", lambda x: 2 ** x, {"x": (E, 0, 6, (2, 2))})
+    case("others_invert_and", lambda x: (~x) & 10, {"x": (E, 0, 15, (4,))})
+    case("others_clip", lambda x: x.clip(5, 10), {"x": (E, 0, 15, (3, 2))})
+    case("others_maximum_tensor", lambda x: np.maximum(x, [[10, 20], [30, 40], [50, 60]]), {"x": (E, 0, 63, (3, 2))})
+    case("others_shape_attrs", lambda x: x + x.shape[0] + x.ndim + x.size, {"x": (E, 0, 15, (3, 2))})
+    case("others_ones_zeros_like", lambda x: x + np.ones_like(x) + np.zeros_like(x), {"x": (E, 0, 15, (2, 3))})
+    table32 = cnp.LookupTable(list(range(32)))
+    case("others_tlu_of_sum", lambda x, y: table32[x + y], {"x": (E, 0, 15, (3,)), "y": (E, 0, 15, (3,))})
+    case("others_cube", lambda x: x ** 3, {"x": (E, 0, 4, ())})
+
 
 def known_answers():
     """Known-answer circuits of the reference (tests/compilation/test_circuit.py:132-192, 307-345;
