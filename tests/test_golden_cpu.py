@@ -76,3 +76,17 @@ def test_golden_wide_crt_lanes(name, clear_backend, monkeypatch):
     for case in doc["cases"]:
         got = clear_engine.run_crt(X, doc, [to_value(a) for a in case["args"]])
         assert same(got, to_value(case["expected"])), name
+
+
+def test_every_operator_family_runs_on_crt_lanes(clear_backend, monkeypatch):
+    """All small reference-generated circuits, forced onto CRT residues (moduli for their own width): every executor
+    handler (broadcasting, indexing, concat, conv2d, sums, mapped tables, ...) works lane-wise and the table expansion
+    over extracted-bit patterns reproduces the reference's clear evaluation."""
+    clear_engine.install_wide(monkeypatch)
+    names = [n for n in SMALL if not n.startswith(("cfg1", "cfg2", "cfg3_", "cfg4", "lin_"))]
+    assert len(names) > 100
+    for name in names:
+        doc = load_golden(name)
+        case = doc["cases"][0]
+        got = clear_engine.run_crt(X, doc, [to_value(a) for a in case["args"]])
+        assert same(got, to_value(case["expected"])), name
