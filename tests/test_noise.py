@@ -67,3 +67,35 @@ def test_selected_parameters_error_rate(cuda_device, bits):
     meas = _log2_std(ph - (exp << np.uint64(63 - p.p)))
     model = 0.5 * math.log2(P.variance_pbs_out(p.n, p.k, p.N, p.pbs_level, p.pbs_base_log, p.glwe_std ** 2))
     assert meas < model + 1.0, (meas, model)
+
+
+@pytest.mark.parametrize("bits", [9, 16])
+def test_wide_lookup_noise_within_model_and_error_free(cuda_device, bits):
+    """Wide (CRT) lookups at the searched 128-bit parameters: every result exact, and the measured output noise of the
+    residue ciphertexts stays below the model the parameter search relies on (which is meant to be conservative) and
+    within 2 bits of it (so that the search is not wasting margin either)."""
+    from concrete_numpy_b200 import wide
+
+    prm = P.select_wide_parameters(bits, 1.0, 1e-6)
+    ks = E.KeySet(prm, cuda_device, seed=5)
+    ev = E.EvalKeys.of(ks)
+    B = 384
+    rng = np.random.default_rng(bits)
+    x = rng.integers(0, 1 << bits, B)
+    table = rng.integers(0, 1 << bits, 1 << bits)
+    luts = wide.build_crt_luts(table, prm.moduli)
+    pool = wide.lut_pool(prm, luts, cuda_device)
+    cts = [E.encrypt_plaintexts(ks, wide.encode_residue(x, m), first_index=i * B) for i, m in enumerate(prm.moduli)]
+    outs = wide.wide_table_lookup(ev, cts, pool, max(luts.shape[2] // prm.N, 1))
+    res, errs = [], []
+    for o, m in zip(outs, prm.moduli):
+        _, ph = E.decrypt(ks, o, return_phase=True)
+        r = wide.decode_residue(ph, m)
+        res.append(r)
+        errs.append((ph - wide.encode_residue(r, m)).view(np.int64).astype(np.float64) / 2.0 ** 64)
+    M = int(np.prod(prm.moduli))
+    assert np.array_equal(wide.crt_combine(res, prm.moduli), table[x] % M)
+    meas = 0.5 * math.log2(float(np.mean(np.concatenate(errs) ** 2)))
+    model = 0.5 * math.log2(P.wide_output_variance(prm))
+    assert model - 2.0 <= meas <= model + 0.25, (meas, model)
+    assert P.estimate_wide_p_error(prm, 1.0) <= 1e-6
