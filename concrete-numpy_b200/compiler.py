@@ -203,11 +203,11 @@ class ServerLambda:
 
     def __init__(self, result: CompilationResult):
         self.result = result
-        self._executors: Dict[str, Executor] = {}
+        self._executors: Dict[tuple, Executor] = {}
 
     def executor(self, device) -> Executor:
         group = _shard_group()
-        key = f"{device}/{id(group) if group is not None else 0}"
+        key = (str(device), group)          # the group object itself: an id() can be reused after collection
         if key not in self._executors:
             self._executors[key] = Executor(self.result.program, self.result.crypto, device, group=group)
         return self._executors[key]

@@ -40,6 +40,9 @@ static size_t plan_smem(const PbsPlanMeta& m, int k, int level) {
 // are used for small batches (latency plans).  Values are indices into all_plans().
 static std::vector<int> fitting_plans(int N, int k, int level) {
     static const std::vector<PbsPlanEntry> plans = all_plans();
+    // development knob, read once: FHE_PBS_ACCTM=0 keeps the accumulator in shared memory (A/B measurements)
+    static const bool use_acctm = [] { const char* e = getenv("FHE_PBS_ACCTM"); return !(e && e[0] == '0'); }();
+    static const bool no_256x2 = [] { const char* e = getenv("FHE_PBS_256X2"); return e && e[0] == '0'; }();
     std::vector<int> out;
     const int logN = ilog2_exact(N);
     if (logN < 8 || logN > 15 || k < 1 || k > 3 || level < 1 || level > 4) return out;
@@ -57,12 +60,22 @@ static std::vector<int> fitting_plans(int N, int k, int level) {
             const size_t smem = plan_smem(m, k, level);
             if (smem > PBS_SMEM_MAX) continue;
             long ctas = (long)(233472 / (smem + 1024));
-            const long by_regs = 256 / m.NT > 0 ? 256 / m.NT : 1;
+            long by_regs = 256 / m.NT > 0 ? 256 / m.NT : 1;      // 255 registers per thread unless __launch_bounds__ says more CTAs
+            if (by_regs < m.minb) by_regs = m.minb;
             if (ctas > by_regs) ctas = by_regs;
             if (m.minb == 1 && ctas > 1) ctas = 1;            // tensor-memory twiddle plans are built for one CTA per SM
             if (ctas < 1) ctas = 1;
             const long threads = ctas * m.NT;
-            if (threads > best_threads) { best_threads = threads; best = (int)i; }
+            if (m.acctm && !use_acctm) continue;
+            if (no_256x2 && m.C == 1 && m.NT == 256 && m.minb == 2) continue;
+            // at equal residency the tensor-memory accumulator plan wins (profiles/r02_*: no remote loads in P1)
+            const bool tie = (threads == best_threads) && best >= 0;
+            // ties: more registers per thread first (lower minb), then the tensor-memory accumulator plan
+            if (threads > best_threads || (tie && m.minb < plans[best].meta.minb) ||
+                (tie && m.minb == plans[best].meta.minb && m.acctm && !plans[best].meta.acctm)) {
+                best_threads = threads;
+                best = (int)i;
+            }
         }
         if (best >= 0) out.push_back(best);
     }

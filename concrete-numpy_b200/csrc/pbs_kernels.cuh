@@ -48,7 +48,7 @@ struct PbsGeom {
 };
 
 // Compile-time FFT plan.  M = R1 * L1, L1 = RA * RB * RF (RA / RB = 1 when absent).
-template <int C_, int LOGR1_, int LRA_, int LRB_, int LRF_, int NT_, int MINB_, int KMAX_>
+template <int C_, int LOGR1_, int LRA_, int LRB_, int LRF_, int NT_, int MINB_, int KMAX_, int ACCTM_ = 0>
 struct PbsPlan {
     static constexpr int C = C_, LOGC = (C_ == 1 ? 0 : C_ == 2 ? 1 : C_ == 4 ? 2 : C_ == 8 ? 3 : 4);
     static constexpr int LOGR1 = LOGR1_, R1 = 1 << LOGR1_;
@@ -74,16 +74,26 @@ struct PbsPlan {
     // quiet but queues behind outstanding global / remote accesses of the SM, so tensor memory holds only the
     // mid-pass twiddles and only in the plans that run one CTA per SM; the others keep them in shared memory.
     static constexpr bool TMEM_TW = (MINB_ == 1);
-    static constexpr int TM_THREAD = TM_A + TM_B;
+    // ACC_TM (cluster plans, k = 1): the accumulator words a thread owns stay in ITS tensor-memory lane (the same
+    // thread reads them in P1 and updates them in P5), and the shared-memory array holds the ROTATED accumulator of
+    // the next CMUX instead: every update is pushed (st.shared::cluster, fire and forget) to the CTA that will need
+    // it as X^a * ACC.  The latency-bound remote loads of P1 become posted stores that drain behind P5.
+    static constexpr bool ACC_TM = (ACCTM_ != 0);
+    static constexpr int ACC_ITEMS = ACC_TM ? (2 << (LOGL1 - LOGC)) / NT_ : 0;     // (k+1)*Q / NT items per thread
+    static constexpr int TM_ACC = ACC_TM ? ACC_ITEMS * 4 * (1 << LOGR1_) : 0;      // 2*R1 u64 per item
+    static constexpr int TM_THREAD = TM_A + TM_B + TM_ACC;
     static constexpr int TM_NEED = (TM_THREAD > 0 ? TM_THREAD : 1) * ((NT_ + 127) / 128);
     static constexpr int TM_CTA = TM_NEED <= 32 ? 32 : TM_NEED <= 64 ? 64 : TM_NEED <= 128 ? 128 : TM_NEED <= 256 ? 256 : 512;
     static_assert(TM_NEED <= 512, "tensor memory holds 512 columns");
     static_assert(C_ == 1 || LOGR1_ == LOGC, "cluster plans use R1 == C");
     static_assert(LRA_ > 0 || LRB_ == 0, "pass B requires pass A");
+    static_assert(!ACC_TM || (C_ > 1 && MINB_ == 1 && KMAX_ == 1 && ((2 << (LOGL1 - LOGC)) % NT_) == 0),
+                  "ACC_TM: cluster plan, one CTA per SM, k = 1, whole items per thread");
 };
 
 struct PbsPlanMeta {       // what the host needs to know about a plan
     int C, logR1, lra, lrb, lrf, NT, minb, kmax, logM;
+    int acctm;             // accumulator in tensor memory + pushed rotated copy (PbsPlan::ACC_TM)
     long smem_fixed;       // bytes of shared memory besides ACC and the work buffers (twiddles live in TMEM)
 };
 
@@ -214,6 +224,9 @@ __device__ __forceinline__ u64 ld_cluster_u64(unsigned addr) {
     asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_cluster_u64(unsigned addr, u64 v) {
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
 __device__ __forceinline__ double2 ld_cluster_f64x2(unsigned addr) {
     double2 v;
     asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
@@ -291,6 +304,7 @@ __device__ __forceinline__ int modswitch_coarse(u64 x, int logN, int theta) {
 struct TwCtx {
     unsigned base;            // tensor-memory allocation base (for dealloc)
     unsigned tA, tB;          // this thread's mid-pass twiddles in tensor memory (TMEM_TW plans)
+    unsigned tAcc;            // this thread's accumulator words in tensor memory (ACC_TM plans)
     const double2 *sA, *sB;   // mid-pass twiddle tables in shared memory (other plans)
     const double2* twT;       // stage-1 twiddles [R1][L1] in global memory (L1/L2 resident)
 };
@@ -318,7 +332,7 @@ __device__ __forceinline__ TwCtx tw_setup(double2* tw_smem, const double2* __res
     tw.twT = twT;
     tw.sA = tw_smem;
     tw.sB = tw_smem + P::TWA;
-    tw.base = tw.tA = tw.tB = 0;
+    tw.base = tw.tA = tw.tB = tw.tAcc = 0;
     if constexpr (P::TMEM_TW) {
         __shared__ unsigned s_tmem_base;
         const int warp = threadIdx.x >> 5;
@@ -330,6 +344,7 @@ __device__ __forceinline__ TwCtx tw_setup(double2* tw_smem, const double2* __res
         const unsigned mine = tw.base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)((warp >> 2) * P::TM_THREAD);
         tw.tA = mine;
         tw.tB = mine + P::TM_A;
+        tw.tAcc = mine + P::TM_A + P::TM_B;
         if constexpr (P::LRA > 0) tw_init_pass<P::LRA, P::LOGL1, P::LOGBUF, P::NT>(tw.tA, tw_mid);
         if constexpr (P::LRB > 0) tw_init_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, P::NT>(tw.tB, tw_mid + P::TWA);
         tmem_wait_st();
@@ -531,22 +546,37 @@ __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* _
             const int hb = base >> P::LOGL1;                      // in [0, 4*R1)
             const int owner = (g.dbg & 2) ? rank : (jj2 >> P::LOGQ);
             const u64* src_local = accc + (jj2 & (Q - 1));
-            const unsigned src_peer = (C > 1) ? mapa_u32(smem_u32(src_local), owner) : 0u;
+            const unsigned src_peer = (C > 1 && !P::ACC_TM) ? mapa_u32(smem_u32(src_local), owner) : 0u;
 #pragma unroll
             for (int half = 0; half < 2; half++) {       // two batches bound the registers in flight
                 u64 rv[R1];
+                unsigned ow[P::ACC_TM ? 2 * R1 : 1];
+                if constexpr (P::ACC_TM) {
+                    // the rotated operand was pushed into `acc` by its producers (sign applied), the thread's own
+                    // words wait in its tensor-memory lane: no remote access on this side of the exchange
+                    TmemIo<2 * R1>::ld(tw.tAcc + (unsigned)((it / NT) * 4 * R1 + half * 2 * R1), ow);
 #pragma unroll
-                for (int e = 0; e < R1; e++) {
-                    const int hjp = (hb + half * R1 + e) & (2 * R1 - 1);
-                    if (C > 1) rv[e] = ld_cluster_u64(src_peer + ((unsigned)hjp << (P::LOGQ + 3)));
-                    else rv[e] = src_local[hjp << P::LOGQ];
+                    for (int e = 0; e < R1; e++) rv[e] = accc[((half * R1 + e) << P::LOGQ) + q];
+                    tmem_wait_ld();
+                } else {
+#pragma unroll
+                    for (int e = 0; e < R1; e++) {
+                        const int hjp = (hb + half * R1 + e) & (2 * R1 - 1);
+                        if (C > 1) rv[e] = ld_cluster_u64(src_peer + ((unsigned)hjp << (P::LOGQ + 3)));
+                        else rv[e] = src_local[hjp << P::LOGQ];
+                    }
                 }
 #pragma unroll
                 for (int e = 0; e < R1; e++) {
                     const int hj = half * R1 + e;
                     const int hjr = (hb + hj) & (4 * R1 - 1);
-                    const u64 own = accc[(hj << P::LOGQ) + q];
-                    const u64 diff = ((hjr >> (P::LOGR1 + 1)) ? (0ULL - rv[e]) : rv[e]) - own;
+                    u64 diff;
+                    if constexpr (P::ACC_TM) {
+                        diff = rv[e] - (((u64)ow[2 * e + 1] << 32) | (u64)ow[2 * e]);
+                    } else {
+                        const u64 own = accc[(hj << P::LOGQ) + q];
+                        diff = ((hjr >> (P::LOGR1 + 1)) ? (0ULL - rv[e]) : rv[e]) - own;
+                    }
                     if (sizeof(ST) == 4) {
                         // level*base_log <= 30: the state only needs bits [nonrep-1, 64) of diff
                         const unsigned top = (unsigned)(diff >> 32);
@@ -645,16 +675,35 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
         const u64* lwe = in + (size_t)ct * (g.n + 1);
         const u64* lut = luts + (size_t)(lut_idx ? lut_idx[ct] : 0) * (k + 1) * N;
         // ---- ACC = X^{-b~} * LUT
+        int a_next = EXT ? modswitch_coarse(lwe[0], g.logN, g.theta) : modswitch(lwe[0], g.logN);
         {
             const int a0 = (2 * N - (EXT ? modswitch_coarse(lwe[g.n], g.logN, g.theta) : modswitch(lwe[g.n], g.logN))) & (2 * N - 1);
+            // ACC_TM: the shared array holds X^{a_0} * ACC, the operand of the first CMUX, ACC itself goes to tensor memory
+            const int a0s = P::ACC_TM ? ((a0 + a_next) & (2 * N - 1)) : a0;
             for (int w = tid; w < (k + 1) * S; w += NT) {
                 const int c = w >> P::LOGS, s = w & (S - 1);
-                const int v = (slot_to_coef<P>(s, rank) - a0) & (2 * N - 1);
+                const int v = (slot_to_coef<P>(s, rank) - a0s) & (2 * N - 1);
                 const u64 x = lut[(size_t)c * N + (v & (N - 1))];
                 acc[w] = (v >> (P::LOGM + 1)) ? (0ULL - x) : x;
             }
+            if constexpr (P::ACC_TM) {
+#pragma unroll 1
+                for (int it = tid; it < ((k + 1) << P::LOGQ); it += NT) {
+                    const int c = it >> P::LOGQ, q = it & (Q - 1);
+                    unsigned ow[4 * R1];
+#pragma unroll
+                    for (int hj = 0; hj < 2 * R1; hj++) {
+                        const int v = ((hj << P::LOGL1) + (rank << P::LOGQ) + q - a0) & (2 * N - 1);
+                        u64 x = lut[(size_t)c * N + (v & (N - 1))];
+                        if (v >> (P::LOGM + 1)) x = 0ULL - x;
+                        ow[2 * hj] = (unsigned)x;
+                        ow[2 * hj + 1] = (unsigned)(x >> 32);
+                    }
+                    TmemIo<4 * R1>::st(tw.tAcc + (unsigned)((it / NT) * 4 * R1), ow);
+                }
+                tmem_wait_st();
+            }
         }
-        int a_next = EXT ? modswitch_coarse(lwe[0], g.logN, g.theta) : modswitch(lwe[0], g.logN);
         csync<C>();
 
         for (int i = 0; i < g.n; i++) {
@@ -810,19 +859,73 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
                 } else
                     stage1_gather<P>(work + ((size_t)o << P::LOGBUF), j2, T, g, z);
                 u64* acco = acc + ((size_t)o << P::LOGS);
+                if constexpr (P::ACC_TM) {
+                    // own words: tensor memory; every updated word is pushed to the CTA that reads it as X^{a'} * ACC in
+                    // the next CMUX: coefficient p = hj*L1 + j2 lands on (p + a') mod N, negated when it wraps once
+                    const bool push = (i + 1 < g.n);
+                    const int u = j2 + (a_next & (P::L1 - 1));
+                    const int j2d = u & (P::L1 - 1);
+                    const int hbd = (a_next >> P::LOGL1) + (u >> P::LOGL1);
+                    const unsigned dst = mapa_u32(smem_u32(acco + (j2d & (Q - 1))), j2d >> P::LOGQ);
 #pragma unroll
-                for (int j1 = 0; j1 < R1; j1++) {
-                    acco[(j1 << P::LOGQ) + q] += f2torus(z[j1].x * g.inv_M);
-                    acco[((R1 + j1) << P::LOGQ) + q] += f2torus(z[j1].y * g.inv_M);
+                    for (int half = 0; half < 2; half++) {
+                        unsigned ow[2 * R1];
+                        const unsigned ta = tw.tAcc + (unsigned)((it / NT) * 4 * R1 + half * 2 * R1);
+                        TmemIo<2 * R1>::ld(ta, ow);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j1 = 0; j1 < R1; j1++) {
+                            const u64 v = (((u64)ow[2 * j1 + 1] << 32) | (u64)ow[2 * j1]) +
+                                          f2torus((half ? z[j1].y : z[j1].x) * g.inv_M);
+                            ow[2 * j1] = (unsigned)v;
+                            ow[2 * j1 + 1] = (unsigned)(v >> 32);
+                            if (push) {
+                                const int bt = (half * R1 + j1 + hbd) & (4 * R1 - 1);
+                                st_cluster_u64(dst + ((unsigned)(bt & (2 * R1 - 1)) << (P::LOGQ + 3)),
+                                               (bt >> (P::LOGR1 + 1)) ? (0ULL - v) : v);
+                            }
+                        }
+                        TmemIo<2 * R1>::st(ta, ow);
+                    }
+                } else {
+#pragma unroll
+                    for (int j1 = 0; j1 < R1; j1++) {
+                        acco[(j1 << P::LOGQ) + q] += f2torus(z[j1].x * g.inv_M);
+                        acco[((R1 + j1) << P::LOGQ) + q] += f2torus(z[j1].y * g.inv_M);
+                    }
                 }
             }
+            if constexpr (P::ACC_TM) tmem_wait_st();
             inv_phase++;
             PBS_PROF(6)
             csync<C>();
             PBS_PROF(7)
         }
         // ---- sample extract coefficient 0 (extended: coefficients 0..nout-1)
-        if (!EXT) {
+        if constexpr (P::ACC_TM) {
+            // the accumulator words are in the owners' tensor-memory lanes
+            const int nout = EXT ? g.nout : 1;
+#pragma unroll 1
+            for (int it = tid; it < ((k + 1) << P::LOGQ); it += NT) {
+                const int c = it >> P::LOGQ, q = it & (Q - 1);
+                unsigned ow[4 * R1];
+                TmemIo<4 * R1>::ld(tw.tAcc + (unsigned)((it / NT) * 4 * R1), ow);
+                tmem_wait_ld();
+                for (int u = 0; u < nout; u++) {
+                    u64* o = out + ((size_t)ct * nout + u) * ((size_t)k * N + 1);
+#pragma unroll
+                    for (int hj = 0; hj < 2 * R1; hj++) {
+                        const int j = (hj << P::LOGL1) + (rank << P::LOGQ) + q;
+                        const u64 v = ((u64)ow[2 * hj + 1] << 32) | (u64)ow[2 * hj];
+                        if (c < k) {
+                            if (j <= u) o[(size_t)c * N + (u - j)] = v;
+                            else o[(size_t)c * N + (N + u - j)] = 0ULL - v;
+                        } else if (j == u)
+                            o[(size_t)k * N] = v;
+                    }
+                }
+            }
+        } else if (!EXT) {
             u64* o = out + (size_t)ct * ((size_t)k * N + 1);
             for (int w = tid; w < (k + 1) * S; w += NT) {
                 const int c = w >> P::LOGS, s = w & (S - 1);
@@ -1168,7 +1271,7 @@ struct PbsLaunchArgs {
 template <class P>
 struct PbsPlanOps {
     static PbsPlanMeta meta() {
-        return PbsPlanMeta{P::C, P::LOGR1, P::LRA, P::LRB, P::LRF, P::NT, P::MINB, P::KMAX, P::LOGM,
+        return PbsPlanMeta{P::C, P::LOGR1, P::LRA, P::LRB, P::LRF, P::NT, P::MINB, P::KMAX, P::LOGM, P::ACC_TM ? 1 : 0,
                            (long)sizeof(double2) * P::TW_SMEM};
     }
     static size_t smem_pbs(const PbsGeom& g) {

@@ -14,6 +14,7 @@ resolved ON THE HOST into int32 row maps once per program ("plans", cached), so 
 kernel launch on device.
 """
 
+import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -27,8 +28,13 @@ from .mlir_text.parser import Op, Program, TType
 
 @dataclass
 class Ct:
-    data: torch.Tensor            # [E, L] int64
+    data: torch.Tensor            # [E, L] int64; when `sharded`: this rank's block of rows only (Executor._part)
     shape: Tuple[int, ...]
+    sharded: bool = False
+
+
+def _numel(shape) -> int:
+    return int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
 
 
 # ------------------------------------------------------------------- analysis -----
@@ -172,9 +178,15 @@ class Executor:
     """Runs one parsed program on one device with one parameter set."""
 
     def __init__(self, program: Program, params: CryptoParams, device, group=None):
-        """`group`: optional torch.distributed process group.  With world size G > 1 every table
-        lookup is sharded BY CIPHERTEXT over the ranks (keys replicated per GPU) and the bootstrapped
-        rows are all-gathered (NCCL over NVLink on GPUs); the cheap linear ops stay replicated."""
+        """`group`: optional torch.distributed process group.  With world size G > 1 every table lookup on at least
+        `shard_min` ciphertexts is sharded BY CIPHERTEXT (keys are replicated per GPU): rank r bootstraps one
+        contiguous block of rows and the result STAYS sharded.  Element-wise ops, further lookups and matmuls whose
+        rows fall inside the blocks consume the local block with no communication; a sum over the sharded axis adds
+        local partial sums with an all-reduce (the u64 wrap-around add is the torus add); an op that reads other
+        elements (conv2d, index / concat / transpose, returning the result) all-gathers the value once (NCCL over
+        NVLink on GPUs; cached on the value).  Values that never went through a sharded lookup -- the arguments, the
+        cheap HBM-bound linear ops on them, and small tensors such as every step of the sequential key-value insert
+        chain -- are replicated: every rank computes them and nothing is sent."""
         self.program = program
         self.params = params
         self.device = torch.device(device)
@@ -190,6 +202,11 @@ class Executor:
         self.moduli = tuple(params.moduli)
         self.lanes = max(len(self.moduli), 1)
         self._res = 0
+        # tensors below this many ciphertexts are replicated, not sharded (CRT circuits shard inside the lookup only)
+        self.shard_min = (1 << 62) if self.moduli else int(os.environ.get("CNP_B200_SHARD_MIN", "64"))
+        self.time_comm = False                      # bench.py: CUDA events around every collective
+        self._comm_events: List[Tuple] = []
+        self._comm = {"allgather_calls": 0, "allgather_bytes": 0, "allreduce_calls": 0, "allreduce_bytes": 0}
         self._plans: Dict[int, dict] = {}          # per-op cached host plans + device uploads
         self._consts: Dict[str, np.ndarray] = {}
         for op in program.ops:
@@ -208,6 +225,78 @@ class Executor:
             "collapse_shape": self._reshape, "expand_shape": self._reshape, "from_elements": self._from_elements,
         }
         self.last_stats = {}
+
+    # -- sharding by ciphertext (world > 1): SURVEY 8e ------------------------------------------------------
+    def _part(self, n: int, rank: Optional[int] = None) -> Tuple[int, int, int]:
+        """Block partition of n rows: (rows per block, first row, end row) of `rank` (default: this rank).  Blocks
+        start on even rows: rows are an odd number of words long, so an odd start would break the 16-byte alignment
+        the kernels vectorise on when a block is a view of a replicated tensor."""
+        r = self.rank if rank is None else rank
+        per = -(-n // self.world)
+        per += per & 1
+        lo = min(r * per, n)
+        return per, lo, min(lo + per, n)
+
+    def _shardable(self, n: int) -> bool:
+        return self.world > 1 and n >= self.shard_min
+
+    def _collective(self, fn, kind: str, nbytes: int):
+        self._comm[kind + "_calls"] += 1
+        self._comm[kind + "_bytes"] += int(nbytes)
+        if self.time_comm and self.device.type == "cuda":
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            self._comm_events.append((e0, e1))
+        else:
+            fn()
+
+    def _full(self, x: Ct) -> torch.Tensor:
+        """All rows of a value on this rank (all-gather of the blocks when it is sharded; cached on the value)."""
+        if not x.sharded:
+            return x.data
+        g = getattr(x, "_gathered", None)
+        if g is None:
+            import torch.distributed as dist
+
+            per = x.data.shape[0]
+            full = torch.empty((per * self.world, self.L), dtype=torch.int64, device=x.data.device)
+            self._collective(lambda: dist.all_gather_into_tensor(full, x.data, group=self.group), "allgather",
+                             full.numel() * 8)
+            g = full[: _numel(x.shape)]
+            x._gathered = g
+        return g
+
+    def _mine(self, x: Ct, lo: int, hi: int) -> torch.Tensor:
+        """Rows [lo, hi) (this rank's block) of a value with as many rows as the result being computed."""
+        return x.data[: hi - lo] if x.sharded else x.data[lo:hi]
+
+    def _sharded(self, rows: torch.Tensor, shape) -> Ct:
+        """Wrap this rank's block of result rows; blocks are padded to the common block size (all-gather needs it)."""
+        per, lo, hi = self._part(_numel(shape))
+        if rows.shape[0] != per:
+            pad = torch.zeros((per, self.L), dtype=torch.int64, device=rows.device)
+            if hi > lo:
+                pad[: hi - lo] = rows[: hi - lo]
+            rows = pad
+        return Ct(rows, tuple(shape), True)
+
+    def _operand(self, x: Ct, row_map: Optional[torch.Tensor], lo: int, hi: int):
+        """(rows, map) with which result rows [lo, hi) read `x`: its own block when the map is the identity, else
+        all of x (gathered if need be) through the block's slice of the map."""
+        if row_map is None:
+            return self._mine(x, lo, hi), None
+        return self._full(x), row_map[lo:hi]
+
+    def _rowwise(self, x: Ct, row_map, shape, fn) -> Ct:
+        """out[e] = fn(x[row_map[e]], e): one result row per (mapped) operand row; fn(rows, map, lo, hi) -> rows."""
+        n = _numel(shape)
+        if not (x.sharded and self._shardable(n)):      # replicated operand: every rank computes all rows, nothing is sent
+            return Ct(fn(self._full(x), row_map, 0, n), tuple(shape))
+        per, lo, hi = self._part(n)
+        d, m = self._operand(x, row_map, lo, hi)
+        return self._sharded(fn(d, m, lo, hi), shape)
 
     # -- device upload helpers (cached per op)
     def _dev(self, arr: Optional[np.ndarray], dtype=None) -> Optional[torch.Tensor]:
@@ -262,6 +351,8 @@ class Executor:
             env.update(self._consts)
         self._ev = ev
         n_pbs = 0
+        self._comm = {k: 0 for k in self._comm}
+        self._comm_events = []
         for op in self.program.ops:
             if op.name == "arith.constant":
                 continue
@@ -280,22 +371,32 @@ class Executor:
                 self._res = 0
             if base in ("apply_lookup_table", "apply_mapped_lookup_table"):
                 n_pbs += op.result_type.size
-        self.last_stats = {"n_pbs": n_pbs}
         results = []
         for r in self.program.returns:
             vals = [env[r] for env in envs]
+            if isinstance(vals[0], Ct):        # every rank returns the complete result
+                vals = [Ct(self._full(v), v.shape) for v in vals]
             if R > 1 and isinstance(vals[0], Ct):
                 results.append(Ct(torch.cat([v.data for v in vals], dim=0), vals[0].shape))
             else:
                 results.append(vals[0])
+        self.last_stats = {"n_pbs": n_pbs, **self._comm}
+        if self._comm_events:
+            torch.cuda.current_stream().synchronize()
+            self.last_stats["comm_ms"] = float(sum(a.elapsed_time(b) for a, b in self._comm_events))
         return results
 
     # ------------------------------------------------------------- elementwise ----
     def _binary_ct(self, op: Op, a: Ct, b: Ct, fn) -> Ct:
         shape = op.result_type.dims
         plan = self._plan(op, lambda: {"ia": self._dev(_row_map(a.shape, shape)), "ib": self._dev(_row_map(b.shape, shape))})
-        n = int(np.prod(shape, dtype=np.int64)) if shape else 1
-        return Ct(fn(a.data, b.data, self.L, plan["ia"], plan["ib"], n), shape)
+        n = _numel(shape)
+        if not ((a.sharded or b.sharded) and self._shardable(n)):
+            return Ct(fn(self._full(a), self._full(b), self.L, plan["ia"], plan["ib"], n), shape)
+        per, lo, hi = self._part(n)
+        da, ia = self._operand(a, plan["ia"], lo, hi)
+        db, ib = self._operand(b, plan["ib"], lo, hi)
+        return self._sharded(fn(da, db, self.L, ia, ib, hi - lo), shape)
 
     def _add_eint(self, op, v):          # node_converter.py:216-242
         return self._binary_ct(op, v[0], v[1], E.lin_add)
@@ -329,30 +430,33 @@ class Executor:
     def _add_eint_int(self, op, v):      # ct + clear: plaintext added to the body only
         shape = op.result_type.dims
         pt = self._clear_operand(op, v[1], shape, encode=True)
-        return Ct(E.lin_add_plain(v[0].data, pt, self.L, self._ct_map(op, v[0], shape)), shape)
+        return self._rowwise(v[0], self._ct_map(op, v[0], shape), shape,
+                             lambda d, m, lo, hi: E.lin_add_plain(d, pt[lo:hi], self.L, m))
 
     def _sub_eint_int(self, op, v):      # ct - clear
         shape = op.result_type.dims
         pt = self._clear_operand(op, v[1], shape, encode=True, negate=True)
-        return Ct(E.lin_add_plain(v[0].data, pt, self.L, self._ct_map(op, v[0], shape)), shape)
+        return self._rowwise(v[0], self._ct_map(op, v[0], shape), shape,
+                             lambda d, m, lo, hi: E.lin_add_plain(d, pt[lo:hi], self.L, m))
 
     def _sub_int_eint(self, op, v):      # clear - ct
         shape = op.result_type.dims
         pt = self._clear_operand(op, v[0], shape, encode=True)
-        return Ct(E.lin_plain_sub(v[1].data, pt, self.L, self._ct_map(op, v[1], shape)), shape)
+        return self._rowwise(v[1], self._ct_map(op, v[1], shape), shape,
+                             lambda d, m, lo, hi: E.lin_plain_sub(d, pt[lo:hi], self.L, m))
 
     def _neg_eint(self, op, v):          # node_converter.py:652-669
-        return Ct(E.lin_neg(v[0].data, self.L), v[0].shape)
+        return self._rowwise(v[0], None, v[0].shape, lambda d, m, lo, hi: E.lin_neg(d, self.L, None, hi - lo))
 
     def _mul_eint_int(self, op, v):      # ct * clear int (all words), node_converter.py:630-650
         shape = op.result_type.dims
         c = self._clear_operand(op, self._weights(v[1]), shape, encode=False)
-        return Ct(E.lin_mul_clear(v[0].data, c, self.L, self._ct_map(op, v[0], shape)), shape)
+        return self._rowwise(v[0], self._ct_map(op, v[0], shape), shape,
+                             lambda d, m, lo, hi: E.lin_mul_clear(d, c[lo:hi], self.L, m))
 
     def _zero(self, op, v):              # trivial encryption of 0: all-zero LWE (node_converter.py:1232-1248)
         shape = op.result_type.dims
-        n = int(np.prod(shape, dtype=np.int64)) if shape else 1
-        return Ct(torch.zeros((n, self.L), dtype=torch.int64, device=self.device), shape)
+        return Ct(torch.zeros((_numel(shape), self.L), dtype=torch.int64, device=self.device), shape)
 
     # --------------------------------------------------------------- lookups ------
     def _tlu(self, op, v):               # keyswitch + PBS per element (node_converter.py:1129-1208)
@@ -372,12 +476,21 @@ class Executor:
                 idx = self._dev(m.astype(np.int32))
             return {"luts": E.from_np_u64(acc, self.device), "idx": idx}
 
-        plan = self._plan(op, build)
-        if self.world == 1:
-            out = E.table_lookup(self._ev, x.data, plan["luts"], plan["idx"])
+        # a table or map that arrives as a clear function argument can change between runs: cache constants only
+        clear_names = [n for n, t in zip(op.operands, op.operand_types) if not t.encrypted]
+        plan = self._plan(op, build) if all(n in self._consts for n in clear_names) else build()
+        shape = op.result_type.dims
+        n = _numel(shape)
+        if not self._shardable(n):
+            return Ct(E.table_lookup(self._ev, self._full(x), plan["luts"], plan["idx"]), shape)
+        # sharded by ciphertext: this rank bootstraps its block, nothing is exchanged
+        per, lo, hi = self._part(n)
+        if hi > lo:
+            idx = None if plan["idx"] is None else plan["idx"][lo:hi]
+            rows = E.table_lookup(self._ev, self._mine(x, lo, hi), plan["luts"], idx)
         else:
-            out = self._tlu_sharded(x.data, plan["luts"], plan["idx"])
-        return Ct(out, op.result_type.dims)
+            rows = torch.zeros((0, self.L), dtype=torch.int64, device=self.device)
+        return self._sharded(rows, shape)
 
     def _tlu_wide(self, op, lanes_v):
         """Lookup on CRT residues (wide.py): bit extraction + circuit bootstrapping once, vertical packing per output
@@ -402,8 +515,9 @@ class Executor:
                 idx = self._dev(m.astype(np.int64))
             return {"pool": wide.lut_pool(p, luts, self.device), "polys": max(luts.shape[2] // p.N, 1), "idx": idx}
 
-        plan = self._plan(op, build)
-        rows = [x.data for x in xs]
+        clear_names = [n for n, t in zip(op.operands, op.operand_types) if not t.encrypted]
+        plan = self._plan(op, build) if all(n in self._consts for n in clear_names) else build()
+        rows = [self._full(x) for x in xs]
         n = rows[0].shape[0]
         if self.world == 1:
             outs = wide.wide_table_lookup(self._ev, rows, plan["pool"], plan["polys"], plan["idx"])
@@ -426,40 +540,79 @@ class Executor:
                 outs.append(full[:n].contiguous())
         return [Ct(o, op.result_type.dims) for o in outs]
 
-    def _tlu_sharded(self, rows: torch.Tensor, luts, idx):
-        """Rank r bootstraps rows [r*per, (r+1)*per) and all ranks gather the result."""
-        import torch.distributed as dist
-
-        n = rows.shape[0]
-        per = (n + self.world - 1) // self.world
-        lo = min(self.rank * per, n)
-        hi = min(lo + per, n)
-        mine = torch.zeros((per, self.L), dtype=torch.int64, device=rows.device)
-        if hi > lo:
-            sub_idx = None if idx is None else idx[lo:hi].contiguous()
-            mine[: hi - lo] = E.table_lookup(self._ev, rows[lo:hi].contiguous(), luts, sub_idx)
-        full = torch.empty((per * self.world, self.L), dtype=torch.int64, device=rows.device)
-        dist.all_gather_into_tensor(full, mine, group=self.group)
-        return full[:n].contiguous()
-
     # ---------------------------------------------------- clear-weighted linear ---
-    def _gather(self, op: Op, x: Ct, build: Callable[[], Tuple[np.ndarray, np.ndarray, Optional[np.ndarray]]]) -> Ct:
+    def _aligned(self, idx: np.ndarray, n_in: int) -> bool:
+        """True when, on EVERY rank, the result rows of its block read only operand rows of its own block (so a
+        sharded operand needs no all-gather).  Decided from the whole index table: all ranks take the same branch."""
+        if not self._shardable(n_in):
+            return False
+        n_out = idx.shape[0]
+        for r in range(self.world):
+            _, lo, hi = self._part(n_out, r)
+            _, xlo, xhi = self._part(n_in, r)
+            sub = idx[lo:hi]
+            ok = sub[sub >= 0]
+            if ok.size and (int(ok.min()) < xlo or int(ok.max()) >= xhi):
+                return False
+        return True
+
+    def _gather(self, op: Op, x: Ct, build: Callable[[], Tuple[np.ndarray, np.ndarray, Optional[np.ndarray]]],
+                reduce_ok: bool = False) -> Ct:
+        """out[e] = sum_j w[e, j] * x[idx[e, j]] (+ bias): dot / matmul / conv2d / sum and friends."""
+        n_in = _numel(x.shape)
+
         def mk():
             idx, w, bias = build()
-            return {"idx": self._dev(idx.astype(np.int32)), "w": self._dev(self._weights(w).astype(np.int64)),
-                    "bias": None if bias is None else self._dev(self._encode(bias))}
+            idx = np.ascontiguousarray(idx).astype(np.int64)
+            d = {"idx": self._dev(idx.astype(np.int32)), "w": self._dev(self._weights(w).astype(np.int64)),
+                 "bias": None if bias is None else self._dev(self._encode(bias)), "n_out": idx.shape[0]}
+            if self.world > 1:
+                n_out = idx.shape[0]
+                d["aligned"] = self._shardable(n_out) and self._aligned(idx, n_in)
+                if d["aligned"]:
+                    _, lo, hi = self._part(n_out)
+                    _, xlo, _ = self._part(n_in)
+                    sub = idx[lo:hi]
+                    d["idx_local"] = self._dev(np.where(sub >= 0, sub - xlo, -1).astype(np.int32))
+                # a reduction over the sharded axis: local partial sums + all-reduce instead of gathering the operand
+                d["reduce"] = (reduce_ok and not d["aligned"] and self._shardable(n_in) and 2 * n_out <= n_in)
+                if d["reduce"]:
+                    _, xlo, xhi = self._part(n_in)
+                    d["idx_part"] = self._dev(np.where((idx >= xlo) & (idx < xhi), idx - xlo, -1).astype(np.int32))
+            return d
 
         clear_names = [n for n, t in zip(op.operands, op.operand_types) if not t.encrypted]
         if all(n in self._consts for n in clear_names):
             plan = self._plan(op, mk)
         else:
             plan = mk()
-        out = E.lin_gather_mac(x.data, plan["idx"], plan["w"], self.L, plan["bias"])
-        return Ct(out, op.result_type.dims)
+        shape = op.result_type.dims
+        n_out = plan["n_out"]
+        if self.world > 1 and x.sharded and plan.get("reduce"):
+            import torch.distributed as dist
+
+            _, xlo, xhi = self._part(n_in)
+            part = E.lin_gather_mac(x.data[: xhi - xlo], plan["idx_part"], plan["w"], self.L, None)
+            self._collective(lambda: dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group), "allreduce",
+                             part.numel() * 8)
+            if plan["bias"] is not None:
+                part = E.lin_add_plain(part, plan["bias"], self.L, None)
+            return Ct(part, shape)
+        if self.world > 1 and x.sharded and plan.get("aligned"):
+            # every block reads its own operand rows only (e.g. a matmul sharded by rows of x): stays sharded
+            per, lo, hi = self._part(n_out)
+            bias = None if plan["bias"] is None else plan["bias"][lo:hi]
+            _, xlo, xhi = self._part(n_in)
+            rows = E.lin_gather_mac(x.data[: max(xhi - xlo, 1)], plan["idx_local"], plan["w"][lo:hi], self.L, bias)
+            return self._sharded(rows, shape)
+        # reads rows of other blocks (conv2d, sums that do not reduce enough, ...): gather the operand once (cached on
+        # the value) and compute every row on every rank -- the linear kernels are HBM-bound and cheap next to a lookup
+        return Ct(E.lin_gather_mac(self._full(x), plan["idx"], plan["w"], self.L, plan["bias"]), shape)
 
     def _dot(self, op, v):               # node_converter.py:497-524 (vector . vector)
         x, c = v
-        return self._gather(op, x, lambda: (np.arange(x.data.shape[0])[None, :], np.asarray(c).reshape(1, -1), None))
+        return self._gather(op, x, lambda: (np.arange(_numel(x.shape))[None, :], np.asarray(c).reshape(1, -1), None),
+                            reduce_ok=True)
 
     def _matmul(self, op, v):            # node_converter.py:596-616, numpy matmul broadcasting
         eint_left = op.name.endswith("matmul_eint_int")
@@ -468,15 +621,24 @@ class Executor:
         out_shape = op.result_type.dims
         if eint_left and len(x.shape) == 2 and W.ndim == 2 and W.shape[0] * 16 * 8 <= 48 * 1024:
             Mr, K = x.shape
+            Nc = W.shape[1]
+            rows_per = Mr // self.world
+            # output row m needs input row m only: with whole rows per block the matmul stays local
+            local_ok = (x.sharded and self._shardable(Mr * Nc) and Mr % self.world == 0
+                        and (rows_per * K) % 2 == 0 and (rows_per * Nc) % 2 == 0)
             wname = op.operands[1]
             if wname in self._consts:
                 Wd = self._plan(op, lambda: {"W": self._dev(self._weights(W))})["W"]
             else:
                 Wd = self._dev(self._weights(W))
-            return Ct(E.matmul_ct_clear(x.data, Wd, Mr, K, W.shape[1], self.L), out_shape)
+            if local_ok:
+                _, xlo, xhi = self._part(Mr * K)
+                rows = E.matmul_ct_clear(self._mine(x, xlo, xhi), Wd, rows_per, K, Nc, self.L)
+                return self._sharded(rows, out_shape)
+            return Ct(E.matmul_ct_clear(self._full(x), Wd, Mr, K, Nc, self.L), out_shape)
 
         def build():
-            xi = np.arange(x.data.shape[0], dtype=np.int64).reshape(x.shape)
+            xi = np.arange(_numel(x.shape), dtype=np.int64).reshape(x.shape)
             a, b = (xi, W) if eint_left else (W, xi)
             a2 = a[None, :] if a.ndim == 1 else a
             b2 = b[:, None] if b.ndim == 1 else b
@@ -506,7 +668,7 @@ class Executor:
             Nb, Cin, H, Wd = x.shape
             F, Cg, KH, KW = W.shape
             _, _, OH, OW = out_shape
-            xi = np.arange(x.data.shape[0], dtype=np.int64).reshape(x.shape)
+            xi = np.arange(_numel(x.shape), dtype=np.int64).reshape(x.shape)
             K = Cg * KH * KW
             idx = np.full((Nb, F, OH, OW, K), -1, dtype=np.int64)
             w = np.zeros((Nb, F, OH, OW, K), dtype=np.int64)
@@ -540,29 +702,42 @@ class Executor:
         out_shape = op.result_type.dims
 
         def build():
-            xi = np.arange(x.data.shape[0], dtype=np.int64).reshape(x.shape)
+            xi = np.arange(_numel(x.shape), dtype=np.int64).reshape(x.shape)
             ax = tuple(axes) if axes else tuple(range(len(x.shape)))
             moved = np.moveaxis(xi, ax, tuple(range(len(x.shape) - len(ax), len(x.shape))))
             K = int(np.prod([x.shape[t] for t in ax], dtype=np.int64)) if ax else 1
             idx = moved.reshape(-1, K)
             return idx, np.ones_like(idx), None
 
-        out = self._gather(op, x, build)
+        out = self._gather(op, x, build, reduce_ok=True)
         _ = keep
-        return Ct(out.data, out_shape)
+        return Ct(out.data, out_shape, out.sharded)
 
     # ------------------------------------------------------------ data movement ---
     def _gather_rows(self, op: Op, srcs: List[Ct], build_index: Callable[[], np.ndarray], shape) -> Ct:
         """out rows = concat(srcs) rows picked by an index map computed with numpy on the host."""
-        plan = self._plan(op, lambda: {"idx": self._dev(build_index().reshape(-1).astype(np.int64))})
-        data = srcs[0].data if len(srcs) == 1 else torch.cat([s.data for s in srcs], dim=0)
+        def mk():
+            idx = build_index().reshape(-1).astype(np.int64)
+            ident = len(srcs) == 1 and idx.size == _numel(srcs[0].shape) and bool(np.array_equal(idx, np.arange(idx.size)))
+            return {"idx": self._dev(idx), "identity": ident}
+
+        plan = self._plan(op, mk)
+        if plan["identity"]:                    # a pure re-interpretation of the same rows keeps its placement
+            return self._reshaped(srcs[0], shape)
+        data = self._full(srcs[0]) if len(srcs) == 1 else torch.cat([self._full(s) for s in srcs], dim=0)
         return Ct(torch.index_select(data, 0, plan["idx"]), shape)
+
+    def _reshaped(self, x: Ct, shape) -> Ct:
+        out = Ct(x.data, tuple(shape), x.sharded)
+        if getattr(x, "_gathered", None) is not None:
+            out._gathered = x._gathered
+        return out
 
     @staticmethod
     def _ids(cts: List[Ct]) -> List[np.ndarray]:
         out, base = [], 0
         for c in cts:
-            n = c.data.shape[0]
+            n = _numel(c.shape)
             out.append(np.arange(base, base + n, dtype=np.int64).reshape(c.shape))
             base += n
         return out
@@ -587,7 +762,7 @@ class Executor:
     def _reshape(self, op, v):           # tensor.collapse_shape / expand_shape (node_converter.py:725-842)
         shape = op.result_type.dims
         if isinstance(v[0], Ct):
-            return Ct(v[0].data, shape)
+            return self._reshaped(v[0], shape)
         return np.asarray(v[0]).reshape(shape)
 
     def _extract(self, op, v):           # tensor.extract with constant indices (node_converter.py:917-1039)
