@@ -46,7 +46,20 @@ _PBS_PLANS = [
 
 
 def pbs_cluster_size(N: int, k: int, level: int) -> int:
-    """Mirror of choose_plan() in csrc/pbs.cu (CTAs per ciphertext, -1 if no on-chip layout fits)."""
+    """CTAs per ciphertext of the bootstrap plan for this shape, -1 if no on-chip layout fits.  Asked from the
+    library itself (fhe_pbs_cluster_size: pure host logic, no GPU needed) so that the parameter search can never
+    pick a shape the kernels reject; the Python mirror below only serves when the library is not built, and
+    tests/test_abi_cpu.py checks that the two agree on every shape."""
+    try:
+        from . import _lib
+
+        return int(_lib.load().fhe_pbs_cluster_size(int(N), int(k), int(level)))
+    except Exception:                                                   # noqa: BLE001  (library absent: CPU-only tooling)
+        return pbs_cluster_size_mirror(N, k, level)
+
+
+def pbs_cluster_size_mirror(N: int, k: int, level: int) -> int:
+    """Mirror of fitting_plans() in csrc/pbs.cu."""
     logM = N.bit_length() - 2
     if N != (2 << logM) or not 8 <= logM + 1 <= 15 or not 1 <= k <= 3 or not 1 <= level <= 4:
         return -1

@@ -94,15 +94,15 @@ def test_plan_selection_and_python_mirror():
         assert lib.fhe_pbs_variant_plan(N, k, level, v, m) == 0
         return tuple(m)
 
-    assert plan(2048, 1, 1)[5] == 128 and plan(2048, 1, 2)[5] == 128          # two 128-thread CTAs per SM
-    assert plan(2048, 1, 3)[5] == 256 and plan(2048, 1, 4)[5] == 256          # one CTA per SM by shared memory
+    assert plan(2048, 1, 1)[5:7] == (256, 2) and plan(2048, 1, 2)[5:7] == (256, 2)   # two 256-thread CTAs per SM at 128 registers
+    assert plan(2048, 1, 3)[5:7] == (256, 1) and plan(2048, 1, 4)[5:7] == (256, 1)   # one CTA per SM by shared memory
     assert plan(32768, 1, 2)[0] == 8 and plan(32768, 1, 3)[0] == 16
     for logN in range(8, 16):
         for k in (1, 2, 3):
             for level in (1, 2, 3, 4):
                 nv = lib.fhe_pbs_num_variants(1 << logN, k, level)
                 c = lib.fhe_pbs_cluster_size(1 << logN, k, level)
-                assert P.pbs_cluster_size(1 << logN, k, level) == c
+                assert P.pbs_cluster_size_mirror(1 << logN, k, level) == c == P.pbs_cluster_size(1 << logN, k, level)
                 assert (nv == 0) == (c < 0)
                 if nv:
                     sizes = [lib.fhe_pbs_variant_cluster_size(1 << logN, k, level, v) for v in range(nv)]
