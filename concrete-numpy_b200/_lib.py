@@ -18,10 +18,11 @@ _SIGS = {
     "fhe_abi_version": (C.c_int, []),
     "fhe_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_long)]),
     "fhe_measure_fp64_peak": (C.c_int, [C.POINTER(C.c_double), _p]),
-    "fhe_keygen_lwe_secret": (C.c_int, [_p, C.c_int, C.c_uint64, C.c_int, _p]),
-    "fhe_keygen_ksk": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, _p]),
-    "fhe_keygen_bsk": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, _p, _p]),
-    "fhe_encrypt_lwe_batch": (C.c_int, [_p, _p, C.c_long, _p, C.c_int, C.c_double, C.c_uint64, C.c_uint64, _p]),
+    "fhe_seed_expand": (C.c_int, [C.c_uint64, _p]),
+    "fhe_keygen_lwe_secret": (C.c_int, [_p, C.c_int, _p, C.c_int, _p]),
+    "fhe_keygen_ksk": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_double, _p, _p]),
+    "fhe_keygen_bsk": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _p, _p, _p]),
+    "fhe_encrypt_lwe_batch": (C.c_int, [_p, _p, C.c_long, _p, C.c_int, C.c_double, _p, C.c_uint64, _p]),
     "fhe_trivial_lwe_batch": (C.c_int, [_p, _p, C.c_long, C.c_int, _p]),
     "fhe_decrypt_lwe_batch": (C.c_int, [_p, _p, _p, C.c_long, _p, C.c_int, C.c_int, _p]),
     "fhe_keyswitch_batch": (C.c_int, [_p, _p, C.c_long, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
@@ -81,6 +82,24 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+KEY_BYTES = 64       # key material: 256-bit secret ChaCha key + 256-bit public-mask key
+
+
+def key_material(seed):
+    """16-word key material for the keygen / encrypt entry points: 64 bytes are used as they are (production:
+    os.urandom(64)); an int is a TEST seed, expanded deterministically by fhe_seed_expand."""
+    key = (C.c_uint32 * 16)()
+    if isinstance(seed, (bytes, bytearray)):
+        if len(seed) != KEY_BYTES:
+            raise ValueError(f"key material is {KEY_BYTES} bytes (secret key, public-mask key)")
+        C.memmove(key, bytes(seed), KEY_BYTES)
+    else:
+        rc = load().fhe_seed_expand(C.c_uint64(int(seed) & ((1 << 64) - 1)), key)
+        if rc != 0:
+            raise FheError("fhe_seed_expand failed")
+    return key
 
 
 LAUNCH_COUNTS = {}   # entry point -> number of calls (each call launches >= 1 CUDA kernel)

@@ -340,8 +340,9 @@ class LibrarySupport(JITSupport):
 # ---------------------------------------------------------------- keys ------------
 
 class KeySetCache:
-    """Insecure key cache (client.py:47-48): keys are a pure function of (seed, parameters), so
-    the cache stores the seed under a digest of the crypto parameters."""
+    """Insecure key cache (client.py:47-48): keys are a pure function of (key material, parameters), so the
+    cache stores the 64 bytes of key material under a digest of the crypto parameters, in a file only its owner
+    can read.  Like the reference's cache it re-uses KEYS; encryption randomness is fresh on every call."""
 
     def __init__(self, path: str):
         self.path = path
@@ -351,14 +352,18 @@ class KeySetCache:
         os.makedirs(path, exist_ok=True)
         return KeySetCache(path)
 
-    def seed_for(self, client_parameters: ClientParameters) -> int:
-        fn = os.path.join(self.path, client_parameters.cache_key() + ".seed")
+    def seed_for(self, client_parameters: ClientParameters) -> bytes:
+        fn = os.path.join(self.path, client_parameters.cache_key() + ".key")
         if os.path.exists(fn):
-            with open(fn, "r", encoding="utf-8") as f:
-                return int(f.read().strip())
-        seed = int.from_bytes(os.urandom(8), "little")
-        with open(fn, "w", encoding="utf-8") as f:
-            f.write(str(seed))
+            with open(fn, "rb") as f:
+                data = f.read()
+            if len(data) == 64:
+                return data
+        seed = E.fresh_key()
+        fd = os.open(fn, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+        with os.fdopen(fd, "wb") as f:
+            f.write(seed)
+        os.chmod(fn, 0o600)
         return seed
 
 
@@ -507,7 +512,7 @@ class ClientSupport:
             elif keyset_cache is not None:
                 seed = keyset_cache.seed_for(client_parameters)
             else:
-                seed = int.from_bytes(os.urandom(8), "little")
+                seed = E.fresh_key()                   # 256-bit secret key + 256-bit public-mask key from the OS
         if not memo:
             return KeySet(E.KeySet(client_parameters.crypto, dev, seed))
         key = (client_parameters.crypto, seed, str(dev))
@@ -537,18 +542,20 @@ class ClientSupport:
             m = a.astype(np.uint64).reshape(-1)
             if m.size and int(m.max()) >= (1 << width):
                 raise RuntimeError(f"argument value does not fit {width} bits")
-            # fresh mask/noise streams for every call: object ids never repeat under one key
+            # mask / noise streams: fresh OS entropy for every call; only a key set made from a TEST seed (explicit
+            # `seed=` / CNP_B200_KEY_SEED: bit-reproducible runs, identical ciphertexts on every rank) derives them
+            # from the seed and a running index
+            det = keyset.keys.deterministic
+            enc_seed = E.derive_key(keyset.keys.seed, 0x5EEDC0DEC0FFEE) if det else None
             if crypto.wide:
                 # one ciphertext per CRT residue, rows residue-major: [residue][element]
                 from . import wide
 
                 pts = np.concatenate([wide.encode_residue(m.astype(np.int64), mod) for mod in crypto.moduli])
-                ct = E.encrypt_plaintexts(keyset.keys, pts, first_index=keyset._enc_counter,
-                                          seed=keyset.keys.seed ^ 0x5EEDC0DEC0FFEE)
+                ct = E.encrypt_plaintexts(keyset.keys, pts, first_index=keyset._enc_counter if det else 0, seed=enc_seed)
                 keyset._enc_counter += int(pts.size)
             else:
-                ct = E.encrypt(keyset.keys, m, first_index=keyset._enc_counter,
-                               seed=keyset.keys.seed ^ 0x5EEDC0DEC0FFEE)
+                ct = E.encrypt(keyset.keys, m, first_index=keyset._enc_counter if det else 0, seed=enc_seed)
                 keyset._enc_counter += int(m.size)
             values.append(Ct(ct, shape))
         return PublicArguments(values)

@@ -48,14 +48,25 @@ __host__ __device__ __forceinline__ u64 splitmix64(u64 x) {
 struct ChaKey {
     u32 w[8];
 };
-static inline ChaKey chacha_key_from_seed(u64 seed) {
-    ChaKey k;
+// Key material of the C ABI: 16 host words = a SECRET 256-bit ChaCha key (secret-key bits, noise) followed by a
+// separate 256-bit key for the PUBLIC masks of BSK / KSK / ciphertexts -- nothing published is a stream of the key
+// that produced the secrets.  Production callers pass 64 bytes of OS entropy.
+struct ChaKeys {
+    ChaKey sec, pub;
+};
+static inline ChaKeys chacha_keys_load(const u32* key16) {
+    ChaKeys k;
+    for (int i = 0; i < 8; i++) { k.sec.w[i] = key16[i]; k.pub.w[i] = key16[8 + i]; }
+    return k;
+}
+// deterministic expansion of a 64-bit TEST seed (fhe_seed_expand; same definition as oracle/tfhe_ref.c)
+#define FHE_PUBLIC_SEED_TWEAK 0xA5A5C3C39696F00FULL
+static inline void chacha_key_from_seed(u64 seed, u32 k[8]) {
     for (int i = 0; i < 4; i++) {
         u64 kw = splitmix64(seed + (u64)i * 0xD1342543DE82EF95ULL);
-        k.w[2 * i] = (u32)kw;
-        k.w[2 * i + 1] = (u32)(kw >> 32);
+        k[2 * i] = (u32)kw;
+        k[2 * i + 1] = (u32)(kw >> 32);
     }
-    return k;
 }
 
 __device__ __forceinline__ u32 rotl32(u32 v, int c) { return __funnelshift_l(v, v, c); }

@@ -2,7 +2,8 @@
 // Replaces ClientSupport.key_set / encrypt_arguments / decrypt_result of the absent
 // concrete-compiler wheel (reference call sites: concrete/numpy/compilation/client.py:106,
 // 178-182, 201).  Every random word comes from the counter-based ChaCha20 streams of
-// common.cuh, so outputs are a pure function of (seed, object index).
+// common.cuh, so outputs are a pure function of (key material, object index); masks (public) and secrets / noise
+// are streams of two different 256-bit keys (ChaKeys).
 #include "common.cuh"
 
 // ---------------------------------------------------------------- secret keys ---
@@ -35,7 +36,7 @@ __device__ __forceinline__ u64 block_sum_u64(u64 v, u64* sh) {
 // mode 1: sk_big[row/level] << (64-(row%level+1)*base_log)   (KSK)
 __global__ void __launch_bounds__(128)
 k_lwe_rows(u64* __restrict__ out, const u64* __restrict__ pt, const u64* __restrict__ sk, int dim,
-           double std, ChaKey key, int mask_dom, int noise_dom, u64 first_id, int mode,
+           double std, ChaKeys keys, int mask_dom, int noise_dom, u64 first_id, int mode,
            const u64* __restrict__ sk_big, int level, int base_log) {
     __shared__ u64 sh[4];
     const long row = blockIdx.x;
@@ -45,7 +46,7 @@ k_lwe_rows(u64* __restrict__ out, const u64* __restrict__ pt, const u64* __restr
     const int nblk = (dim + 7) >> 3;
     for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
         u64 w[8];
-        chacha20_block(key, stream_id(mask_dom, id), (u64)b, w);
+        chacha20_block(keys.pub, stream_id(mask_dom, id), (u64)b, w);
 #pragma unroll
         for (int t = 0; t < 8; t++) {
             int j = b * 8 + t;
@@ -64,7 +65,7 @@ k_lwe_rows(u64* __restrict__ out, const u64* __restrict__ pt, const u64* __restr
             long i = row / level;
             m = sk_big[i] ? (1ULL << (64 - (lv + 1) * base_log)) : 0ULL;
         }
-        dst[dim] = total + m + gaussian_torus(key, stream_id(noise_dom, id), 0, std);
+        dst[dim] = total + m + gaussian_torus(keys.sec, stream_id(noise_dom, id), 0, std);
     }
 }
 
@@ -101,7 +102,7 @@ k_decrypt(u64* __restrict__ phase, u64* __restrict__ msg, const u64* __restrict_
 // --------------------------------------------------------------- BSK ------------
 // step 1: masks (uniform) and body initialised with noise; grid = (rows, k+1)
 __global__ void __launch_bounds__(256)
-k_bsk_init(u64* __restrict__ bsk, int k, int N, double std, ChaKey key) {
+k_bsk_init(u64* __restrict__ bsk, int k, int N, double std, ChaKeys keys) {
     const long R = blockIdx.x;
     const int c = blockIdx.y;
     u64* poly = bsk + ((size_t)R * (k + 1) + c) * N;
@@ -109,13 +110,13 @@ k_bsk_init(u64* __restrict__ bsk, int k, int N, double std, ChaKey key) {
         const int nblk = N >> 3;
         for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
             u64 w[8];
-            chacha20_block(key, stream_id(DOM_BSK_MASK, (u64)R), (u64)c * nblk + b, w);
+            chacha20_block(keys.pub, stream_id(DOM_BSK_MASK, (u64)R), (u64)c * nblk + b, w);
 #pragma unroll
             for (int t = 0; t < 8; t++) poly[b * 8 + t] = w[t];
         }
     } else {
         for (int t = threadIdx.x; t < N; t += blockDim.x)
-            poly[t] = gaussian_torus(key, stream_id(DOM_BSK_NOISE, (u64)R), (u64)t, std);
+            poly[t] = gaussian_torus(keys.sec, stream_id(DOM_BSK_NOISE, (u64)R), (u64)t, std);
     }
 }
 
@@ -167,19 +168,27 @@ __global__ void k_list_ones(const u64* __restrict__ sk_glwe, int k, int N, int* 
 // ------------------------------------------------------------------ C ABI -------
 extern "C" {
 
-int fhe_keygen_lwe_secret(u64* sk, int dim, u64 seed, int domain, void* stream) {
-    if (dim <= 0 || (domain != DOM_SK_SMALL && domain != DOM_SK_BIG)) FHE_FAIL(2, "keygen_lwe_secret: bad arguments");
-    k_keygen_secret<<<(dim + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sk, dim, chacha_key_from_seed(seed), domain);
+// test / reproducibility mode only: 64-bit seed -> the 16 words of key material (production: 64 bytes of OS entropy)
+int fhe_seed_expand(u64 seed, u32* key16) {
+    if (!key16) FHE_FAIL(2, "seed_expand: null output");
+    chacha_key_from_seed(seed, key16);
+    chacha_key_from_seed(seed ^ FHE_PUBLIC_SEED_TWEAK, key16 + 8);
+    return 0;
+}
+
+int fhe_keygen_lwe_secret(u64* sk, int dim, const u32* key16, int domain, void* stream) {
+    if (dim <= 0 || !key16 || (domain != DOM_SK_SMALL && domain != DOM_SK_BIG)) FHE_FAIL(2, "keygen_lwe_secret: bad arguments");
+    k_keygen_secret<<<(dim + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sk, dim, chacha_keys_load(key16).sec, domain);
     FHE_CHECK_LAUNCH();
     return 0;
 }
 
 int fhe_keygen_ksk(u64* ksk, const u64* sk_big, int kN, const u64* sk_small, int n, int level,
-                   int base_log, double std, u64 seed, void* stream) {
-    if (kN <= 0 || n <= 0 || level <= 0 || level * base_log >= 64) FHE_FAIL(2, "keygen_ksk: bad arguments");
+                   int base_log, double std, const u32* key16, void* stream) {
+    if (kN <= 0 || n <= 0 || !key16 || level <= 0 || level * base_log >= 64) FHE_FAIL(2, "keygen_ksk: bad arguments");
     long rows = (long)kN * level;
     k_lwe_rows<<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(
-        ksk, nullptr, sk_small, n, std, chacha_key_from_seed(seed), DOM_KSK_MASK, DOM_KSK_NOISE, 0,
+        ksk, nullptr, sk_small, n, std, chacha_keys_load(key16), DOM_KSK_MASK, DOM_KSK_NOISE, 0,
         1, sk_big, level, base_log);
     FHE_CHECK_LAUNCH();
     return 0;
@@ -187,8 +196,8 @@ int fhe_keygen_ksk(u64* ksk, const u64* sk_big, int kN, const u64* sk_small, int
 
 // scratch: device buffer of at least (k*N + k) int32 words
 int fhe_keygen_bsk(u64* bsk, const u64* sk_small, int n, const u64* sk_glwe, int k, int N,
-                   int level, int base_log, double std, u64 seed, int* scratch, void* stream) {
-    if (n <= 0 || k <= 0 || ilog2_exact(N) < 4 || N < 256 || level <= 0 || level * base_log >= 64)
+                   int level, int base_log, double std, const u32* key16, int* scratch, void* stream) {
+    if (n <= 0 || k <= 0 || !key16 || ilog2_exact(N) < 4 || N < 256 || level <= 0 || level * base_log >= 64)
         FHE_FAIL(2, "keygen_bsk: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     long rows = (long)n * level * (k + 1);
@@ -196,7 +205,7 @@ int fhe_keygen_bsk(u64* bsk, const u64* sk_small, int n, const u64* sk_glwe, int
     int* ones_cnt = scratch + (size_t)k * N;
     k_list_ones<<<k, 32, 0, st>>>(sk_glwe, k, N, ones, ones_cnt);
     FHE_CHECK_LAUNCH();
-    k_bsk_init<<<dim3((unsigned)rows, k + 1), 256, 0, st>>>(bsk, k, N, std, chacha_key_from_seed(seed));
+    k_bsk_init<<<dim3((unsigned)rows, k + 1), 256, 0, st>>>(bsk, k, N, std, chacha_keys_load(key16));
     FHE_CHECK_LAUNCH();
     k_bsk_body<<<dim3((unsigned)rows, N / 256), 256, 0, st>>>(bsk, ones, ones_cnt, k, N);
     FHE_CHECK_LAUNCH();
@@ -206,11 +215,11 @@ int fhe_keygen_bsk(u64* bsk, const u64* sk_small, int n, const u64* sk_glwe, int
 }
 
 int fhe_encrypt_lwe_batch(u64* ct, const u64* plaintexts, long B, const u64* sk, int dim, double std,
-                          u64 seed, u64 first_index, void* stream) {
-    if (B < 0 || dim <= 0) FHE_FAIL(2, "encrypt_lwe_batch: bad arguments");
+                          const u32* key16, u64 first_index, void* stream) {
+    if (B < 0 || dim <= 0 || !key16) FHE_FAIL(2, "encrypt_lwe_batch: bad arguments");
     if (B == 0) return 0;
     k_lwe_rows<<<(unsigned)B, 128, 0, (cudaStream_t)stream>>>(
-        ct, plaintexts, sk, dim, std, chacha_key_from_seed(seed), DOM_ENC_MASK, DOM_ENC_NOISE,
+        ct, plaintexts, sk, dim, std, chacha_keys_load(key16), DOM_ENC_MASK, DOM_ENC_NOISE,
         first_index, 0, nullptr, 1, 1);
     FHE_CHECK_LAUNCH();
     return 0;

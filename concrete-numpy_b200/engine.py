@@ -66,6 +66,21 @@ class CryptoParams:
         return asdict(self)
 
 
+def fresh_key() -> bytes:
+    """64 bytes of OS entropy: a 256-bit secret ChaCha key and a separate 256-bit key for the public masks."""
+    return os.urandom(_lib.KEY_BYTES)
+
+
+def derive_key(seed, tweak: int):
+    """Independent key material for another object under the same root: a TEST seed (int) is xored with the tweak
+    (the oracle does the same), real key material is re-hashed with it."""
+    if isinstance(seed, (bytes, bytearray)):
+        import hashlib
+
+        return hashlib.sha512(bytes(seed) + int(tweak).to_bytes(8, "little")).digest()
+    return (int(seed) ^ int(tweak)) & ((1 << 64) - 1)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -86,16 +101,20 @@ def from_np_u64(a: np.ndarray, device) -> torch.Tensor:
 class KeySet:
     """Device-resident secret + evaluation keys for one parameter set."""
 
-    def __init__(self, params: CryptoParams, device, seed: int, keep_std_bsk: bool = False):
+    def __init__(self, params: CryptoParams, device, seed=None, keep_std_bsk: bool = False):
+        """`seed`: None = 64 bytes of OS entropy (production); 64 bytes = that key material; an int = a TEST seed
+        (deterministic expansion, bit-reproducible against the oracle and identical on every rank)."""
         self.params = params
         self.device = torch.device(device)
-        self.seed = int(seed)
+        self.seed = fresh_key() if seed is None else (bytes(seed) if isinstance(seed, (bytes, bytearray)) else int(seed))
+        self.deterministic = isinstance(self.seed, int)
+        key = _lib.key_material(self.seed)
         p = params
         dev = self.device
         with torch.cuda.device(dev):
             st = _stream()
             self.sk_big = torch.empty(p.big_dim, dtype=torch.int64, device=dev)
-            _lib.call("fhe_keygen_lwe_secret", self.sk_big.data_ptr(), p.big_dim, self.seed, DOM_SK_BIG, st)
+            _lib.call("fhe_keygen_lwe_secret", self.sk_big.data_ptr(), p.big_dim, key, DOM_SK_BIG, st)
             if p.linear_only:           # no table lookups: nothing to bootstrap or keyswitch with
                 self.sk_small = torch.empty(0, dtype=torch.int64, device=dev)
                 self.ksk = torch.empty((0, 0, 1), dtype=torch.int64, device=dev)
@@ -105,15 +124,15 @@ class KeySet:
                 torch.cuda.current_stream().synchronize()
                 return
             self.sk_small = torch.empty(p.n, dtype=torch.int64, device=dev)
-            _lib.call("fhe_keygen_lwe_secret", self.sk_small.data_ptr(), p.n, self.seed, DOM_SK_SMALL, st)
+            _lib.call("fhe_keygen_lwe_secret", self.sk_small.data_ptr(), p.n, key, DOM_SK_SMALL, st)
             self.ksk = torch.empty((p.big_dim, p.ks_level, p.n + 1), dtype=torch.int64, device=dev)
             _lib.call("fhe_keygen_ksk", self.ksk.data_ptr(), self.sk_big.data_ptr(), p.big_dim,
-                      self.sk_small.data_ptr(), p.n, p.ks_level, p.ks_base_log, p.lwe_std, self.seed, st)
+                      self.sk_small.data_ptr(), p.n, p.ks_level, p.ks_base_log, p.lwe_std, key, st)
             bsk_std = torch.empty((p.n, p.pbs_level, p.k + 1, p.k + 1, p.N), dtype=torch.int64, device=dev)
             scratch = torch.empty(p.k * p.N + p.k + 8, dtype=torch.int32, device=dev)
             _lib.call("fhe_keygen_bsk", bsk_std.data_ptr(), self.sk_small.data_ptr(), p.n,
                       self.sk_big.data_ptr(), p.k, p.N, p.pbs_level, p.pbs_base_log, p.glwe_std,
-                      self.seed, scratch.data_ptr(), st)
+                      key, scratch.data_ptr(), st)
             self.bsk_std = bsk_std if keep_std_bsk else None
             self.bsk_f = bsk_std_to_fourier(bsk_std, p)
             self.pfksk = None
@@ -222,8 +241,16 @@ class EvalKeys:
 
 # ------------------------------------------------------------------ client side ----
 
-def encrypt(keyset: KeySet, messages: np.ndarray, first_index: int = 0, seed: Optional[int] = None) -> torch.Tensor:
-    """Encode `m << (63 - p)` and LWE-encrypt each message under the big key."""
+def _enc_key(keyset: KeySet, seed):
+    """Mask / noise key material of one encryption call: FRESH OS entropy unless the caller asks for reproducible
+    streams (a TEST seed, or a deterministic key set with an explicit index window)."""
+    if seed is None:
+        seed = fresh_key()
+    return _lib.key_material(seed)
+
+
+def encrypt(keyset: KeySet, messages: np.ndarray, first_index: int = 0, seed=None) -> torch.Tensor:
+    """Encode `m << (63 - p)` and LWE-encrypt each message under the big key.  `seed` None: fresh randomness."""
     p = keyset.params
     dev = keyset.device
     m = np.ascontiguousarray(np.asarray(messages).reshape(-1).astype(np.uint64))
@@ -231,11 +258,11 @@ def encrypt(keyset: KeySet, messages: np.ndarray, first_index: int = 0, seed: Op
     ct = torch.empty((m.size, p.ct_words), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _lib.call("fhe_encrypt_lwe_batch", ct.data_ptr(), pt.data_ptr(), m.size, keyset.sk_big.data_ptr(),
-                  p.big_dim, p.glwe_std, keyset.seed if seed is None else int(seed), int(first_index), _stream())
+                  p.big_dim, p.glwe_std, _enc_key(keyset, seed), int(first_index), _stream())
     return ct
 
 
-def encrypt_plaintexts(keyset: KeySet, plaintexts: np.ndarray, first_index: int = 0, seed: Optional[int] = None) -> torch.Tensor:
+def encrypt_plaintexts(keyset: KeySet, plaintexts: np.ndarray, first_index: int = 0, seed=None) -> torch.Tensor:
     """LWE-encrypt already encoded u64 plaintexts under the big key (CRT residues of the wide path)."""
     p = keyset.params
     dev = keyset.device
@@ -244,7 +271,7 @@ def encrypt_plaintexts(keyset: KeySet, plaintexts: np.ndarray, first_index: int 
     ct = torch.empty((pt_np.size, p.ct_words), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _lib.call("fhe_encrypt_lwe_batch", ct.data_ptr(), pt.data_ptr(), pt_np.size, keyset.sk_big.data_ptr(),
-                  p.big_dim, p.glwe_std, keyset.seed if seed is None else int(seed), int(first_index), _stream())
+                  p.big_dim, p.glwe_std, _enc_key(keyset, seed), int(first_index), _stream())
     return ct
 
 

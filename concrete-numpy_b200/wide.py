@@ -154,7 +154,7 @@ def build_crt_luts(tables: np.ndarray, moduli: Sequence[int]) -> np.ndarray:
 
 # ------------------------------------------------------------------ keys -------------------
 
-def keygen_packing_key(params, sk_big: torch.Tensor, seed: int) -> torch.Tensor:
+def keygen_packing_key(params, sk_big: torch.Tensor, seed) -> torch.Tensor:
     """[(kN + PF_PAD), pf_level, (k+1)^2 N]: fhe_keygen_bsk on the extended big key (s, -1, 0...)."""
     p = params
     dev = sk_big.device
@@ -166,7 +166,7 @@ def keygen_packing_key(params, sk_big: torch.Tensor, seed: int) -> torch.Tensor:
     scratch = torch.empty(p.k * p.N + p.k + 8, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _lib.call("fhe_keygen_bsk", key.data_ptr(), ext.data_ptr(), kN + PF_PAD, sk_big.data_ptr(), p.k, p.N,
-                  p.pf_level, p.pf_base_log, p.glwe_std, (int(seed) ^ PF_SEED_XOR) & ((1 << 64) - 1),
+                  p.pf_level, p.pf_base_log, p.glwe_std, _lib.key_material(E.derive_key(seed, PF_SEED_XOR)),
                   scratch.data_ptr(), E._stream())
     return key
 

@@ -37,15 +37,20 @@ int fhe_device_info(int* sm_count, int* cc_major, int* cc_minor, long* total_mem
 int fhe_measure_fp64_peak(double* tflops, void* stream);
 
 /* ---- key generation: replaces ClientSupport.key_set (client.py:96-106) ---------------
- * Keys are a pure function of (seed, parameters): counter-based ChaCha20 streams.
+ * Keys are a pure function of (key material, parameters): counter-based ChaCha20 streams.
+ * key16: HOST pointer to 16 words = a SECRET 256-bit ChaCha key (secret-key bits, noise) followed by a separate
+ * 256-bit key for the PUBLIC masks of BSK / KSK / ciphertexts.  Production callers fill it with 64 bytes of OS
+ * entropy (os.urandom); fhe_seed_expand() is the deterministic 64-bit-seed expansion for tests and for
+ * regenerating identical keys on every rank of a benchmark.
  * domain: 1 = small LWE key (dimension n), 2 = big key (k*N, the flattened GLWE key). */
-int fhe_keygen_lwe_secret(uint64_t* sk, int dim, uint64_t seed, int domain, void* stream);
+int fhe_seed_expand(uint64_t seed, uint32_t* key16);
+int fhe_keygen_lwe_secret(uint64_t* sk, int dim, const uint32_t* key16, int domain, void* stream);
 /* KSK [kN][level][n+1]: row (i, lv) encrypts sk_big[i] * 2^(64-(lv+1)*base_log) under sk_small */
 int fhe_keygen_ksk(uint64_t* ksk, const uint64_t* sk_big, int kN, const uint64_t* sk_small, int n,
-                   int level, int base_log, double std, uint64_t seed, void* stream);
+                   int level, int base_log, double std, const uint32_t* key16, void* stream);
 /* standard-domain BSK [n][level][k+1][k+1][N]; scratch: >= k*N + k int32 words */
 int fhe_keygen_bsk(uint64_t* bsk, const uint64_t* sk_small, int n, const uint64_t* sk_glwe, int k,
-                   int N, int level, int base_log, double std, uint64_t seed, int* scratch,
+                   int N, int level, int base_log, double std, const uint32_t* key16, int* scratch,
                    void* stream);
 /* Fourier-domain BSK conversion on device; layout owned by the bootstrap kernel.
  * fhe_bsk_fourier_elems() = number of (re, im) double pairs of the output buffer. */
@@ -57,7 +62,7 @@ int fhe_bsk_to_fourier(void* bsk_f /* double2* */, const uint64_t* bsk_std, int 
 /* ---- encrypt / decrypt: replace ClientSupport.encrypt_arguments / decrypt_result -----
  * (client.py:178-182, 201).  plaintexts are already encoded (m << (63 - p)). */
 int fhe_encrypt_lwe_batch(uint64_t* ct /* [B][dim+1] */, const uint64_t* plaintexts /* [B] */,
-                          long B, const uint64_t* sk, int dim, double std, uint64_t seed,
+                          long B, const uint64_t* sk, int dim, double std, const uint32_t* key16,
                           uint64_t first_index, void* stream);
 int fhe_trivial_lwe_batch(uint64_t* ct, const uint64_t* plaintexts, long B, int dim, void* stream);
 /* phase[e] = body - <a, s>; msg[e] = phase decoded at p bits + 1 padding bit (either may be NULL) */

@@ -65,10 +65,21 @@ class Oracle:
                               C.c_uint64(count), C.c_double(std), out.ctypes.data_as(_u64p))
         return out
 
+    # -- key material: 16 words (secret ChaCha key, public-mask key); an int is a TEST seed expanded deterministically
+    def key_material(self, seed):
+        key = (C.c_uint32 * 16)()
+        if isinstance(seed, (bytes, bytearray)):
+            if len(seed) != 64:
+                raise ValueError("key material is 64 bytes (secret key, public-mask key)")
+            C.memmove(key, bytes(seed), 64)
+        else:
+            self.lib.ref_seed_expand(C.c_uint64(int(seed) & ((1 << 64) - 1)), key)
+        return key
+
     # -- keys
     def keygen_lwe_secret(self, dim, seed, domain):
         sk = np.empty(dim, dtype=np.uint64)
-        self.lib.ref_keygen_lwe_secret(sk.ctypes.data_as(_u64p), C.c_int(dim), C.c_uint64(seed),
+        self.lib.ref_keygen_lwe_secret(sk.ctypes.data_as(_u64p), C.c_int(dim), self.key_material(seed),
                                        C.c_int(domain))
         return sk
 
@@ -79,7 +90,7 @@ class Oracle:
         s2, p2 = self._u64(sk_glwe)
         self.lib.ref_keygen_bsk(bsk.ctypes.data_as(_u64p), p1, C.c_int(n), p2, C.c_int(k),
                                 C.c_int(N), C.c_int(level), C.c_int(base_log), C.c_double(std),
-                                C.c_uint64(seed))
+                                self.key_material(seed))
         return bsk
 
     def keygen_ksk(self, sk_big, sk_small, level, base_log, std, seed):
@@ -89,7 +100,7 @@ class Oracle:
         s2, p2 = self._u64(sk_small)
         self.lib.ref_keygen_ksk(ksk.ctypes.data_as(_u64p), p1, C.c_int(kN), p2, C.c_int(n),
                                 C.c_int(level), C.c_int(base_log), C.c_double(std),
-                                C.c_uint64(seed))
+                                self.key_material(seed))
         return ksk
 
     # -- encrypt / decrypt
@@ -99,7 +110,7 @@ class Oracle:
         dim = len(sk)
         ct = np.empty((len(pt), dim + 1), dtype=np.uint64)
         self.lib.ref_encrypt_lwe_batch(ct.ctypes.data_as(_u64p), pp, C.c_long(len(pt)), ps,
-                                       C.c_int(dim), C.c_double(std), C.c_uint64(seed),
+                                       C.c_int(dim), C.c_double(std), self.key_material(seed),
                                        C.c_uint64(first_index))
         return ct
 

@@ -27,8 +27,12 @@
  *   stands for gadget factor 2^(64-(lv+1)*base_log);
  *   KSK: [kN][level][n+1], same level convention.
  *
- * Randomness: a counter-based ChaCha20 generator (seed, stream, index) so that the
- * CUDA path can reproduce every key / mask / noise word bit-for-bit.  Gaussian
+ * Randomness: a counter-based ChaCha20 generator (key, stream, index) so that the
+ * CUDA path can reproduce every key / mask / noise word bit-for-bit.  Key material is
+ * 16 words: a SECRET 256-bit ChaCha key (secret-key bits, noise) followed by a separate
+ * 256-bit key for the PUBLIC masks of BSK / KSK / ciphertexts, so that nothing published
+ * is a stream of the key that produced the secrets.  Production callers pass 64 bytes of
+ * OS entropy; `ref_seed_expand` is the deterministic 64-bit-seed expansion of the tests.  Gaussian
  * noise is Box-Muller evaluated with +,-,*,/,sqrt,fma only (all correctly rounded
  * IEEE-754 operations) so CPU and GPU agree to the last bit.
  */
@@ -57,16 +61,29 @@ static inline u64 splitmix64(u64 x) {
     a += b; d ^= a; d = ROTL32(d, 8);                                         \
     c += d; b ^= c; b = ROTL32(b, 7);
 
-/* One ChaCha20 block (RFC 8439 round function; 64-bit block counter in words
- * 12-13, 64-bit stream id in words 14-15). */
-static void chacha20_block(u64 seed, u64 stream, u64 block, u32 out[16]) {
-    u32 st[16], x[16];
-    st[0] = 0x61707865u; st[1] = 0x3320646eu; st[2] = 0x79622d32u; st[3] = 0x6b206574u;
+/* deterministic expansion of a 64-bit TEST seed into one 256-bit ChaCha key */
+static void key_from_seed(u64 seed, u32 k[8]) {
     for (int i = 0; i < 4; i++) {
         u64 kw = splitmix64(seed + (u64)i * 0xD1342543DE82EF95ULL);
-        st[4 + 2 * i] = (u32)kw;
-        st[5 + 2 * i] = (u32)(kw >> 32);
+        k[2 * i] = (u32)kw;
+        k[2 * i + 1] = (u32)(kw >> 32);
     }
+}
+#define PUBLIC_SEED_TWEAK 0xA5A5C3C39696F00FULL
+/* test / reproducibility mode only: 64-bit seed -> (secret key, public-mask key) */
+void ref_seed_expand(u64 seed, u32 key16[16]) {
+    key_from_seed(seed, key16);
+    key_from_seed(seed ^ PUBLIC_SEED_TWEAK, key16 + 8);
+}
+#define KSEC(key16) (key16)
+#define KPUB(key16) ((key16) + 8)
+
+/* One ChaCha20 block (RFC 8439 round function; 64-bit block counter in words
+ * 12-13, 64-bit stream id in words 14-15). */
+static void chacha20_block(const u32 key[8], u64 stream, u64 block, u32 out[16]) {
+    u32 st[16], x[16];
+    st[0] = 0x61707865u; st[1] = 0x3320646eu; st[2] = 0x79622d32u; st[3] = 0x6b206574u;
+    for (int i = 0; i < 8; i++) st[4 + i] = key[i];
     st[12] = (u32)block; st[13] = (u32)(block >> 32);
     st[14] = (u32)stream; st[15] = (u32)(stream >> 32);
     memcpy(x, st, sizeof(x));
@@ -79,28 +96,30 @@ static void chacha20_block(u64 seed, u64 stream, u64 block, u32 out[16]) {
     for (int i = 0; i < 16; i++) out[i] = x[i] + st[i];
 }
 
-/* idx-th 64-bit word of stream `stream` under `seed` (8 words per block). */
-static inline u64 rng_u64(u64 seed, u64 stream, u64 idx) {
+/* idx-th 64-bit word of stream `stream` under `key` (8 words per block). */
+static inline u64 rng_u64(const u32 *key, u64 stream, u64 idx) {
     u32 blk[16];
-    chacha20_block(seed, stream, idx >> 3, blk);
+    chacha20_block(key, stream, idx >> 3, blk);
     int w = (int)(idx & 7) * 2;
     return (u64)blk[w] | ((u64)blk[w + 1] << 32);
 }
 
 /* fill out[0..count) with words idx0.. of a stream, one block at a time */
-static void rng_fill(u64 seed, u64 stream, u64 idx0, u64 count, u64 *out) {
+static void rng_fill(const u32 *key, u64 stream, u64 idx0, u64 count, u64 *out) {
     u32 blk[16];
     u64 cur = ~0ULL;
     for (u64 j = 0; j < count; j++) {
         u64 idx = idx0 + j;
-        if ((idx >> 3) != cur) { cur = idx >> 3; chacha20_block(seed, stream, cur, blk); }
+        if ((idx >> 3) != cur) { cur = idx >> 3; chacha20_block(key, stream, cur, blk); }
         int w = (int)(idx & 7) * 2;
         out[j] = (u64)blk[w] | ((u64)blk[w + 1] << 32);
     }
 }
 
 void ref_rng_u64(u64 seed, u64 stream, u64 idx0, u64 count, u64 *out) {
-    rng_fill(seed, stream, idx0, count, out);
+    u32 k[8];
+    key_from_seed(seed, k);
+    rng_fill(k, stream, idx0, count, out);
 }
 
 /* stream-id domains */
@@ -182,8 +201,8 @@ static double det_cos2pi(double u) { /* u in [0,1) -> cos(2*pi*u) */
 
 /* j-th Gaussian sample of a noise stream, as a torus (u64, wrapping) value with
  * standard deviation `std` (relative to q = 2^64). */
-static u64 gaussian_torus(u64 seed, u64 stream, u64 j, double std) {
-    u64 x1 = rng_u64(seed, stream, 2 * j), x2 = rng_u64(seed, stream, 2 * j + 1);
+static u64 gaussian_torus(const u32 *key, u64 stream, u64 j, double std) {
+    u64 x1 = rng_u64(key, stream, 2 * j), x2 = rng_u64(key, stream, 2 * j + 1);
     double u1 = (double)((x1 >> 11) + 1) * 0x1.0p-53; /* (0,1] */
     double u2 = (double)(x2 >> 11) * 0x1.0p-53;       /* [0,1) */
     double r = sqrt(-2.0 * det_log(u1));
@@ -193,15 +212,17 @@ static u64 gaussian_torus(u64 seed, u64 stream, u64 j, double std) {
 }
 
 void ref_gaussian(u64 seed, u64 stream, u64 j0, u64 count, double std, u64 *out) {
-    for (u64 j = 0; j < count; j++) out[j] = gaussian_torus(seed, stream, j0 + j, std);
+    u32 k[8];
+    key_from_seed(seed, k);
+    for (u64 j = 0; j < count; j++) out[j] = gaussian_torus(k, stream, j0 + j, std);
 }
 
 /* ------------------------------------------------------------- keygen ---- */
 
 /* binary secret key: bit i = bit (i%64) of word i/64 of stream (domain, 0) */
-void ref_keygen_lwe_secret(u64 *sk, int dim, u64 seed, int domain) {
+void ref_keygen_lwe_secret(u64 *sk, int dim, const u32 *key16, int domain) {
     for (int i = 0; i < dim; i++)
-        sk[i] = (rng_u64(seed, STREAM(domain, 0), (u64)(i >> 6)) >> (i & 63)) & 1ULL;
+        sk[i] = (rng_u64(KSEC(key16), STREAM(domain, 0), (u64)(i >> 6)) >> (i & 63)) & 1ULL;
 }
 
 /* out += a * s in Z[X]/(X^N+1), s binary (one u64 per coefficient) */
@@ -216,17 +237,17 @@ static void negacyclic_mul_binary_acc(u64 *out, const u64 *a, const u64 *s, int 
 
 /* GLWE encryption of zero, row index R selects the mask / noise streams */
 static void glwe_encrypt_zero(u64 *ct, const u64 *sk_glwe, int k, int N, double std,
-                              u64 seed, u64 R) {
+                              const u32 *key16, u64 R) {
     u64 *body = ct + (size_t)k * N;
-    for (int t = 0; t < N; t++) body[t] = gaussian_torus(seed, STREAM(DOM_BSK_NOISE, R), (u64)t, std);
+    for (int t = 0; t < N; t++) body[t] = gaussian_torus(KSEC(key16), STREAM(DOM_BSK_NOISE, R), (u64)t, std);
     for (int c = 0; c < k; c++) {
-        rng_fill(seed, STREAM(DOM_BSK_MASK, R), (u64)c * N, (u64)N, ct + (size_t)c * N);
+        rng_fill(KPUB(key16), STREAM(DOM_BSK_MASK, R), (u64)c * N, (u64)N, ct + (size_t)c * N);
         negacyclic_mul_binary_acc(body, ct + (size_t)c * N, sk_glwe + (size_t)c * N, N);
     }
 }
 
 void ref_keygen_bsk(u64 *bsk, const u64 *sk_small, int n, const u64 *sk_glwe, int k, int N,
-                    int level, int base_log, double std, u64 seed) {
+                    int level, int base_log, double std, const u32 *key16) {
     const size_t row_words = (size_t)(k + 1) * N;
     const long rows = (long)n * level * (k + 1);
 #pragma omp parallel for schedule(dynamic, 4)
@@ -235,7 +256,7 @@ void ref_keygen_bsk(u64 *bsk, const u64 *sk_small, int n, const u64 *sk_glwe, in
         int lv = (int)((R / (k + 1)) % level);
         int i = (int)(R / ((long)(k + 1) * level));
         u64 *row = bsk + (size_t)R * row_words;
-        glwe_encrypt_zero(row, sk_glwe, k, N, std, seed, (u64)R);
+        glwe_encrypt_zero(row, sk_glwe, k, N, std, key16, (u64)R);
         /* key entries are 0/1 for an LWE key; the extended key of the packing keyswitch (wide-integer
          * path, ref_keygen_bsk is reused for it) also holds -1 for the body slot */
         row[(size_t)r * N] += sk_small[i] * (1ULL << (64 - (lv + 1) * base_log));
@@ -243,15 +264,15 @@ void ref_keygen_bsk(u64 *bsk, const u64 *sk_small, int n, const u64 *sk_glwe, in
 }
 
 void ref_keygen_ksk(u64 *ksk, const u64 *sk_big, int kN, const u64 *sk_small, int n,
-                    int level, int base_log, double std, u64 seed) {
+                    int level, int base_log, double std, const u32 *key16) {
     const long rows = (long)kN * level;
 #pragma omp parallel for schedule(static)
     for (long R = 0; R < rows; R++) {
         int lv = (int)(R % level);
         int i = (int)(R / level);
         u64 *row = ksk + (size_t)R * (n + 1);
-        rng_fill(seed, STREAM(DOM_KSK_MASK, R), 0, (u64)n, row);
-        u64 body = gaussian_torus(seed, STREAM(DOM_KSK_NOISE, R), 0, std);
+        rng_fill(KPUB(key16), STREAM(DOM_KSK_MASK, R), 0, (u64)n, row);
+        u64 body = gaussian_torus(KSEC(key16), STREAM(DOM_KSK_NOISE, R), 0, std);
         for (int j = 0; j < n; j++) if (sk_small[j]) body += row[j];
         if (sk_big[i]) body += 1ULL << (64 - (lv + 1) * base_log);
         row[n] = body;
@@ -261,13 +282,13 @@ void ref_keygen_ksk(u64 *ksk, const u64 *sk_big, int kN, const u64 *sk_small, in
 /* ------------------------------------------------- encrypt / decrypt ------ */
 
 void ref_encrypt_lwe_batch(u64 *ct, const u64 *pt, long B, const u64 *sk, int dim, double std,
-                           u64 seed, u64 first_index) {
+                           const u32 *key16, u64 first_index) {
 #pragma omp parallel for schedule(static)
     for (long e = 0; e < B; e++) {
         u64 *row = ct + (size_t)e * (dim + 1);
         u64 id = first_index + (u64)e;
-        rng_fill(seed, STREAM(DOM_ENC_MASK, id), 0, (u64)dim, row);
-        u64 body = pt[e] + gaussian_torus(seed, STREAM(DOM_ENC_NOISE, id), 0, std);
+        rng_fill(KPUB(key16), STREAM(DOM_ENC_MASK, id), 0, (u64)dim, row);
+        u64 body = pt[e] + gaussian_torus(KSEC(key16), STREAM(DOM_ENC_NOISE, id), 0, std);
         for (int j = 0; j < dim; j++) if (sk[j]) body += row[j];
         row[dim] = body;
     }

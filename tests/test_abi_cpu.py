@@ -108,3 +108,36 @@ def test_plan_selection_and_python_mirror():
                     sizes = [lib.fhe_pbs_variant_cluster_size(1 << logN, k, level, v) for v in range(nv)]
                     assert sizes == sorted(sizes) and sizes[0] == c == plan(1 << logN, k, level)[0]
     assert lib.fhe_pbs_variant_plan(2048, 1, 1, 99, (C.c_int * 8)()) != 0
+
+
+def test_key_material_and_cache_file_mode(oracle, tmp_path):
+    """Key material is 512 bits (secret ChaCha key + separate public-mask key): 64 caller bytes are used as they are,
+    an int is the deterministic TEST expansion (identical in the library and the oracle); the insecure key cache keeps
+    its file private to the owner."""
+    import stat
+
+    import pytest
+
+    from concrete_numpy_b200 import _lib, compiler as cc, engine as E
+
+    k1, k2 = _lib.key_material(5), _lib.key_material(5)
+    assert list(k1) == list(k2) and list(k1) == list(oracle.key_material(5))
+    assert list(k1)[:8] != list(k1)[8:] and list(k1) != list(_lib.key_material(6))
+    raw = os.urandom(64)
+    assert bytes(_lib.key_material(raw)) == raw and bytes(oracle.key_material(raw)) == raw
+    with pytest.raises(ValueError):
+        _lib.key_material(b"too short")
+    assert E.derive_key(7, 3) == 4
+    d = E.derive_key(raw, 3)
+    assert len(d) == 64 and d != raw and d == E.derive_key(raw, 3) and d != E.derive_key(raw, 4)
+    assert len(E.fresh_key()) == 64 and E.fresh_key() != E.fresh_key()
+
+    class FakeParams:
+        @staticmethod
+        def cache_key():
+            return "abc"
+
+    cache = cc.KeySetCache.new(str(tmp_path / "cache"))
+    s1, s2 = cache.seed_for(FakeParams()), cache.seed_for(FakeParams())
+    assert s1 == s2 and len(s1) == 64
+    assert stat.S_IMODE(os.stat(tmp_path / "cache" / "abc.key").st_mode) == 0o600

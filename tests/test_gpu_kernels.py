@@ -4,6 +4,8 @@ Integer / byte work (keygen, encryption, keyswitch, linear ops) must be BIT-EXAC
 The programmable bootstrap runs an fp64 FFT: its outputs must decrypt to the exact table value and
 stay within a stated torus distance of the oracle's output on the same inputs (tolerance below).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -57,6 +59,32 @@ def test_encrypt_decrypt_bit_exact(oracle, cuda_device):
     # trivial ciphertexts
     tv = E.trivial(p, m[:5], cuda_device)
     assert np.array_equal(E.to_np_u64(tv), oracle.trivial(m[:5] << np.uint64(63 - p.p), p.big_dim))
+
+
+def test_key_material_entropy_and_fresh_encryption_randomness(oracle, cuda_device):
+    """Production key sets take 64 bytes of OS entropy (bit-exact against the oracle given the same bytes), two key
+    sets never share keys, the public masks are not a stream of the secret key, and two encryptions of the same
+    message under one key set never share mask or noise (ciphertext differences must not reveal plaintext differences)."""
+    p = small_params()
+    raw = os.urandom(64)
+    ks = E.KeySet(p, cuda_device, seed=raw, keep_std_bsk=True)
+    assert not ks.deterministic
+    sk_s = oracle.keygen_lwe_secret(p.n, raw, 1)
+    sk_b = oracle.keygen_lwe_secret(p.big_dim, raw, 2)
+    assert np.array_equal(E.to_np_u64(ks.sk_small), sk_s) and np.array_equal(E.to_np_u64(ks.sk_big), sk_b)
+    assert np.array_equal(E.to_np_u64(ks.ksk), oracle.keygen_ksk(sk_b, sk_s, p.ks_level, p.ks_base_log, p.lwe_std, raw))
+    # same secret half, different public half: same secret keys, different masks
+    other = E.KeySet(p, cuda_device, seed=raw[:32] + os.urandom(32))
+    assert np.array_equal(E.to_np_u64(other.sk_big), sk_b)
+    assert not np.array_equal(E.to_np_u64(other.ksk)[:, :, :-1], E.to_np_u64(ks.ksk)[:, :, :-1])
+    a, b = E.KeySet(p, cuda_device), E.KeySet(p, cuda_device)       # default: fresh entropy
+    assert not np.array_equal(E.to_np_u64(a.sk_big), E.to_np_u64(b.sk_big))
+    m = np.arange(16, dtype=np.uint64) % (1 << p.p)
+    c1, c2 = E.to_np_u64(E.encrypt(ks, m)), E.to_np_u64(E.encrypt(ks, m))
+    assert not np.array_equal(c1[:, :-1], c2[:, :-1])                # fresh masks on every call
+    assert len(set((c1[:, 0] - c2[:, 0]).tolist())) == 16
+    assert np.array_equal(E.decrypt(ks, E.from_np_u64(c1, cuda_device)), m)
+    assert np.array_equal(E.decrypt(ks, E.from_np_u64(c2, cuda_device)), m)
 
 
 @pytest.mark.parametrize("B", [1, 5, 33, 600])
