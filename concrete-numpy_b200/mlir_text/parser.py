@@ -143,7 +143,35 @@ def parse_attr(text: str):
             raise MlirSyntaxError(f"dense attribute without type: {text!r}")
         ttype = parse_type(rest[1:])
         body = body.strip()
-        if body.startswith("["):
+        if body.startswith('"0x') or body.startswith('"0X'):
+            # the MLIR printer switches to a hex blob above 64 elements (every lookup table of >= 7 bits, most weight
+            # matrices): raw little-endian element storage, iN stored in ceil(N/8) bytes, i1 bit-packed; a single
+            # element is a splat.  Values are sign-extended from N bits -- what the decimal form would have printed.
+            if not body.endswith('"'):
+                raise MlirSyntaxError(f"unterminated hex dense attribute: {text[:60]!r}...")
+            try:
+                raw = bytes.fromhex(body[3:-1])
+            except ValueError as e:
+                raise MlirSyntaxError(f"bad hex dense attribute: {e}") from None
+            n = int(np.prod(ttype.dims, dtype=np.int64)) if ttype.dims else 1
+            w = int(ttype.width)
+            if w == 1:
+                bits = np.unpackbits(np.frombuffer(raw, dtype=np.uint8), bitorder="little")
+                vals = [int(b) for b in bits[:n]] if len(raw) == (n + 7) // 8 else [int(bits[0])]
+            else:
+                bw = (w + 7) // 8
+                if len(raw) % bw:
+                    raise MlirSyntaxError(f"hex dense attribute of {len(raw)} bytes for {bw}-byte elements")
+                vals = []
+                for i in range(len(raw) // bw):
+                    v = int.from_bytes(raw[i * bw:(i + 1) * bw], "little") & ((1 << w) - 1)
+                    vals.append(v - (1 << w) if v >> (w - 1) else v)
+            if len(vals) == 1 and n != 1:
+                vals = vals * n
+            if len(vals) != n:
+                raise MlirSyntaxError(f"hex dense attribute holds {len(vals)} elements, type wants {n}")
+            data = np.array(vals, dtype=object)
+        elif body.startswith("["):
             data = np.array(ast.literal_eval(body), dtype=object)
         elif body in ("true", "false"):
             data = np.full(ttype.dims, 1 if body == "true" else 0, dtype=object)

@@ -231,7 +231,7 @@ def test_pbs_plan_variants_agree(cuda_device, p_bits, n, k, N, level, base_log):
     ev = E.EvalKeys.of(ks)
     assert len(ev.variant_clusters) >= 2 and ev.variant_clusters[0] == _lib.load().fhe_pbs_cluster_size(N, k, level)
     rng = np.random.default_rng(N + 1)
-    B = 9
+    B = 64
     m = rng.integers(0, 1 << p_bits, B).astype(np.uint64)
     table = rng.integers(0, 1 << p_bits, (1, 1 << p_bits))
     luts = E.from_np_u64(E.build_lut_accumulators(p, table), cuda_device)
@@ -243,7 +243,14 @@ def test_pbs_plan_variants_agree(cuda_device, p_bits, n, k, N, level, base_log):
         got, ph = E.decrypt(ks, out, return_phase=True)
         assert np.array_equal(got, exp), (v, ev.variant_clusters[v])
         stds.append((ph - (exp << np.uint64(63 - p_bits))).view(np.int64).astype(np.float64).std())
-    assert max(stds) <= 2.0 * min(stds) + 2.0 ** 20, stds
+    # The variants factor the FFT differently (more, smaller passes on larger clusters), so the fp64 rounding term of
+    # the output noise differs between them; each must stay within the tolerance (variance <= 2x) of the noise model
+    # that the parameter search relies on (params.variance_pbs_out, calibrated on the published fp64-FFT law)
+    from concrete_numpy_b200 import params as P
+
+    model_std = (P.variance_pbs_out(n, k, N, level, base_log, p.glwe_std ** 2) ** 0.5) * 2.0 ** 64
+    assert max(stds) <= (2.0 ** 0.5) * model_std + 2.0 ** 20, (stds, model_std)
+    assert max(stds) <= 4.0 * min(stds) + 2.0 ** 20, stds
     best = max(v for v, c in enumerate(ev.variant_clusters) if v == 0 or c <= 8)
     assert ev.variant_for_batch(1) == best and ev.variant_for_batch(100000) == 0
     assert all(c >= 1 for c in ev._capacity)
