@@ -593,6 +593,15 @@ def _server_call(server_lambda: ServerLambda, public_arguments: PublicArguments,
     enc = [v for v in public_arguments.values if isinstance(v, Ct)]
     device = enc[0].data.device if enc else evaluation_keys.bsk_f.device
     ex = server_lambda.executor(device)
-    with torch.cuda.device(device):
+    with _device_context(device):
         outs = ex.run(evaluation_keys.on(device), list(public_arguments.values))
     return PublicResult(outs)
+
+
+def _device_context(device):
+    """torch.cuda.device(...) for a CUDA device; a no-op for the CPU tensors of the host-logic tests (which swap the
+    engine for tests/clear_engine.py -- the product engine itself raises without CUDA)."""
+    import contextlib
+
+    dev = torch.device(device)
+    return torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()

@@ -35,18 +35,10 @@ int fhe_device_info(int* sm_count, int* cc_major, int* cc_minor, long* total_mem
 }
 
 // returns measured fp64 FMA throughput in TFLOP/s (2 flops per FMA) through *tflops
-int fhe_measure_fp64_peak(double* tflops, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    int dev = 0, sms = 0;
-    FHE_CUDA(cudaGetDevice(&dev));
-    FHE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    double* sink = nullptr;
-    FHE_CUDA(cudaMalloc(&sink, 8));
+static int measure_fp64_peak_impl(double* tflops, cudaStream_t st, double* sink, cudaEvent_t e0, cudaEvent_t e1, int sms) {
     const int iters = 1 << 16, blocks = sms * 8;
-    cudaEvent_t e0, e1;
-    FHE_CUDA(cudaEventCreate(&e0));
-    FHE_CUDA(cudaEventCreate(&e1));
     k_dfma_probe<<<blocks, 256, 0, st>>>(sink, iters, 1.0);   // warm-up
+    FHE_CHECK_LAUNCH();
     double best = 0.0;
     for (int rep = 0; rep < 3; rep++) {
         FHE_CUDA(cudaEventRecord(e0, st));
@@ -59,11 +51,30 @@ int fhe_measure_fp64_peak(double* tflops, void* stream) {
         double tf = fl / (ms * 1e-3) / 1e12;
         if (tf > best) best = tf;
     }
-    FHE_CUDA(cudaEventDestroy(e0));
-    FHE_CUDA(cudaEventDestroy(e1));
-    FHE_CUDA(cudaFree(sink));
     *tflops = best;
     return 0;
+}
+
+int fhe_measure_fp64_peak(double* tflops, void* stream) {
+    if (!tflops) FHE_FAIL(2, "measure_fp64_peak: null output");
+    int dev = 0, sms = 0;
+    FHE_CUDA(cudaGetDevice(&dev));
+    FHE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* sink = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = 0;
+    cudaError_t ce = cudaMalloc(&sink, 8);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e1);
+    if (ce != cudaSuccess) {
+        snprintf(g_fhe_err, sizeof(g_fhe_err), "measure_fp64_peak: %s", cudaGetErrorString(ce));
+        rc = 1000 + (int)ce;
+    } else
+        rc = measure_fp64_peak_impl(tflops, (cudaStream_t)stream, sink, e0, e1, sms);
+    if (e0) cudaEventDestroy(e0);          // released on every path
+    if (e1) cudaEventDestroy(e1);
+    if (sink) cudaFree(sink);
+    return rc;
 }
 
 }  // extern "C"

@@ -131,10 +131,16 @@ static int get_plan(int n, int k, int N, int level, int base_log, int variant, c
             add_pass(m.lra, logL1);
             add_pass(m.lrb, logL1 - m.lra);
             if (tm.empty()) tm.push_back(make_double2(1.0, 0.0));
-            FHE_CUDA(cudaMalloc(&tb.twT, sizeof(double2) * tT.size()));
-            FHE_CUDA(cudaMalloc(&tb.tw_mid, sizeof(double2) * tm.size()));
-            FHE_CUDA(cudaMemcpy(tb.twT, tT.data(), sizeof(double2) * tT.size(), cudaMemcpyHostToDevice));
-            FHE_CUDA(cudaMemcpy(tb.tw_mid, tm.data(), sizeof(double2) * tm.size(), cudaMemcpyHostToDevice));
+            tb.twT = tb.tw_mid = nullptr;
+            cudaError_t ce = cudaMalloc(&tb.twT, sizeof(double2) * tT.size());
+            if (ce == cudaSuccess) ce = cudaMalloc(&tb.tw_mid, sizeof(double2) * tm.size());
+            if (ce == cudaSuccess) ce = cudaMemcpy(tb.twT, tT.data(), sizeof(double2) * tT.size(), cudaMemcpyHostToDevice);
+            if (ce == cudaSuccess) ce = cudaMemcpy(tb.tw_mid, tm.data(), sizeof(double2) * tm.size(), cudaMemcpyHostToDevice);
+            if (ce != cudaSuccess) {                       // nothing half-built stays behind
+                if (tb.twT) cudaFree(tb.twT);
+                if (tb.tw_mid) cudaFree(tb.tw_mid);
+                FHE_FAIL(1000 + (int)ce, "pbs: twiddle tables: %s", cudaGetErrorString(ce));
+            }
             g_tables[{dev, pi}] = tb;
         } else
             tb = it->second;
@@ -147,10 +153,11 @@ static int get_plan(int n, int k, int N, int level, int base_log, int variant, c
     g.theta = 0;
     g.nout = 1;
     {
-        const char* e = getenv("FHE_PBS_STAGGER");
-        g.stagger = e ? atoi(e) : 0;
-        e = getenv("FHE_PBS_DBG");
-        g.dbg = e ? atoi(e) : 0;
+        // development knobs (ablation bits, start-up stagger): read ONCE per process, 0 unless set before the first launch
+        static const int env_stagger = [] { const char* e = getenv("FHE_PBS_STAGGER"); return e ? atoi(e) : 0; }();
+        static const int env_dbg = [] { const char* e = getenv("FHE_PBS_DBG"); return e ? atoi(e) : 0; }();
+        g.stagger = env_stagger;
+        g.dbg = env_dbg;
     }
     for (int j1 = 0; j1 < 16; j1++) {
         long double ang = M_PIl * (long double)j1 / (2.0L * R1);

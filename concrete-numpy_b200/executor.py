@@ -15,6 +15,7 @@ kernel launch on device.
 """
 
 import os
+import threading
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -204,6 +205,7 @@ class Executor:
         self._res = 0
         # tensors below this many ciphertexts are replicated, not sharded (CRT circuits shard inside the lookup only)
         self.shard_min = (1 << 62) if self.moduli else int(os.environ.get("CNP_B200_SHARD_MIN", "64"))
+        self._run_lock = threading.Lock()
         self.time_comm = False                      # bench.py: CUDA events around every collective
         self._comm_events: List[Tuple] = []
         self._comm = {"allgather_calls": 0, "allgather_bytes": 0, "allreduce_calls": 0, "allreduce_bytes": 0}
@@ -329,7 +331,12 @@ class Executor:
 
     # ---------------------------------------------------------------- run ---------
     def run(self, ev: EvalKeys, args: List) -> List:
-        """args: one entry per function argument (Ct for encrypted, numpy array / int for clear)."""
+        """args: one entry per function argument (Ct for encrypted, numpy array / int for clear).  One run at a
+        time per executor (the evaluation keys and the CRT lane of a run are executor state)."""
+        with self._run_lock:
+            return self._run(ev, args)
+
+    def _run(self, ev: EvalKeys, args: List) -> List:
         R = self.lanes
         envs: List[Dict[str, object]] = [{} for _ in range(R)]
         for (name, t), a in zip(self.program.args, args):
@@ -721,7 +728,9 @@ class Executor:
             ident = len(srcs) == 1 and idx.size == _numel(srcs[0].shape) and bool(np.array_equal(idx, np.arange(idx.size)))
             return {"idx": self._dev(idx), "identity": ident}
 
-        plan = self._plan(op, mk)
+        # index operands that arrive as clear function arguments can change between runs: cache constants only
+        clear_names = [n for n, t in zip(op.operands, op.operand_types) if not t.encrypted]
+        plan = self._plan(op, mk) if all(n in self._consts for n in clear_names) else mk()
         if plan["identity"]:                    # a pure re-interpretation of the same rows keeps its placement
             return self._reshaped(srcs[0], shape)
         data = self._full(srcs[0]) if len(srcs) == 1 else torch.cat([self._full(s) for s in srcs], dim=0)

@@ -90,15 +90,69 @@ def decode(body_u64, p):
     return ((t >> np.uint64(1)) + (t & np.uint64(1))) & np.uint64((1 << (p + 1)) - 1)
 
 
+def _trivial_rows(bodies_u64, L):
+    """[E, L] rows with zero masks and the given bodies (a clear 'ciphertext' of L torus words)."""
+    out = np.zeros((bodies_u64.size, L), dtype=np.uint64)
+    out[:, -1] = bodies_u64
+    return _t(out)
+
+
 def table_lookup(ev, ct, luts, lut_idx=None):
     p = ev.params.p
-    m = decode(_u(ct)[:, -1], p).astype(np.int64)
+    cu = _u(ct)
+    m = decode(cu[:, -1], p).astype(np.int64)
     tables = _u(luts)
     which = np.zeros(m.size, dtype=np.int64) if lut_idx is None else lut_idx.numpy().astype(np.int64)
     neg = m >= (1 << p)                       # padding bit set: the bootstrap is negacyclic
     val = tables[which, np.where(neg, m - (1 << p), m)]
     val = np.where(neg, np.uint64(0) - val, val)
-    return _t((val << np.uint64(63 - p))[:, None])
+    return _trivial_rows(val << np.uint64(63 - p), cu.shape[1])
+
+
+# ---- client side + keys: stand-ins for engine.KeySet / EvalKeys / encrypt / decrypt, so that compiler.py (and through
+# it the reference's own Client / Server / Circuit classes) can run end to end on the CPU in the host-logic tests ----
+
+from concrete_numpy_b200.engine import CryptoParams, derive_key, fresh_key  # noqa: E402,F401  (pure-Python helpers)
+
+
+class KeySet:
+    def __init__(self, params, device, seed=None, keep_std_bsk=False):
+        self.params = params
+        self.device = torch.device("cpu")
+        self.seed = fresh_key() if seed is None else seed
+        self.deterministic = isinstance(self.seed, int)
+        self.sk_big = torch.zeros(max(params.big_dim, 1), dtype=torch.int64)
+        self.sk_small = torch.zeros(max(params.n, 1), dtype=torch.int64)
+        self.ksk = torch.zeros((1, 1, 2), dtype=torch.int64)
+        self.bsk_std = None
+        self.bsk_f = torch.zeros((4, 2), dtype=torch.float64)
+        self.pfksk = None
+
+
+class EvalKeys:
+    def __init__(self, params, bsk_f, ksk, pfksk=None):
+        self.params, self.bsk_f, self.ksk, self.pfksk = params, bsk_f, ksk, pfksk
+
+    @staticmethod
+    def of(keyset):
+        return EvalKeys(keyset.params, keyset.bsk_f, keyset.ksk, keyset.pfksk)
+
+
+def encrypt(keyset, messages, first_index=0, seed=None):
+    p = keyset.params
+    m = np.ascontiguousarray(np.asarray(messages).reshape(-1).astype(np.uint64))
+    return _trivial_rows(m << np.uint64(63 - p.p), p.ct_words)
+
+
+def encrypt_plaintexts(keyset, plaintexts, first_index=0, seed=None):
+    pt = np.ascontiguousarray(np.asarray(plaintexts).reshape(-1).astype(np.uint64))
+    return _trivial_rows(pt, keyset.params.ct_words)
+
+
+def decrypt(keyset, ct, return_phase=False):
+    phase = _u(ct.contiguous())[:, -1].copy()
+    msg = decode(phase, keyset.params.p)
+    return (msg, phase) if return_phase else msg
 
 
 # ---- wide integers (CRT residues): clear stand-ins for concrete_numpy_b200.wide.{lut_pool, wide_table_lookup} ----
