@@ -38,57 +38,121 @@ k_flat(u64* __restrict__ out, const u64* __restrict__ a, const u64* __restrict__
 // OP: 0 add, 1 sub, 2 neg, 3 copy + plaintext on body, 4 multiply by clear int,
 //     5 plaintext - ct (sub_int_eint): out = -a, body += pt
 template <int OP>
+__device__ __forceinline__ u64 row_op(u64 x, u64 y, u64 s, bool last) {
+    if (OP == 0) return x + y;
+    if (OP == 1) return x - y;
+    if (OP == 2) return 0ULL - x;
+    if (OP == 3) return x + (last ? s : 0ULL);
+    if (OP == 4) return x * s;
+    return (0ULL - x) + (last ? s : 0ULL);
+}
+
+// Rows are L = k*N+1 words long (odd), so consecutive rows alternate between 16-byte aligned and 8 bytes off.  When the
+// rows an output row reads share its phase (always the case for identity maps), the row moves as 16-byte vectors with a
+// scalar head / tail word; otherwise every thread keeps four independent 8-byte accesses in flight.
+template <int OP>
 __global__ void __launch_bounds__(256)
 k_rows(u64* __restrict__ out, const u64* __restrict__ a, const u64* __restrict__ b,
        const int* __restrict__ ia, const int* __restrict__ ib, const u64* __restrict__ scal,
        int L) {
     const long e = blockIdx.x;
     const u64* ra = a + (size_t)(ia ? ia[e] : e) * L;
-    const u64* rb = (OP <= 1) ? b + (size_t)(ib ? ib[e] : e) * L : nullptr;
+    const u64* rb = (OP <= 1) ? b + (size_t)(ib ? ib[e] : e) * L : ra;
     u64* ro = out + (size_t)e * L;
     const u64 s = (OP >= 3) ? scal[e] : 0ULL;
-    for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < L; t += gridDim.y * blockDim.x) {
-        u64 x = ra[t], r;
-        if (OP == 0) r = x + rb[t];
-        else if (OP == 1) r = x - rb[t];
-        else if (OP == 2) r = 0ULL - x;
-        else if (OP == 3) r = x + ((t == L - 1) ? s : 0ULL);
-        else if (OP == 4) r = x * s;
-        else r = (0ULL - x) + ((t == L - 1) ? s : 0ULL);
-        ro[t] = r;
+    const int nthr = gridDim.y * blockDim.x, tid = blockIdx.y * blockDim.x + threadIdx.x;
+    const unsigned pa = (unsigned)((uintptr_t)ra & 15), pb = (unsigned)((uintptr_t)rb & 15), po = (unsigned)((uintptr_t)ro & 15);
+    if (pa == po && pb == po) {
+        const int head = po ? 1 : 0;                        // one scalar word brings the row to a 16-byte boundary
+        if (tid == 0 && head) ro[0] = row_op<OP>(ra[0], rb[0], s, L == 1);
+        const int nvec = (L - head) >> 1;
+        const ulonglong2* va = reinterpret_cast<const ulonglong2*>(ra + head);
+        const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(rb + head);
+        ulonglong2* vo = reinterpret_cast<ulonglong2*>(ro + head);
+        for (int v = tid; v < nvec; v += nthr) {
+            const ulonglong2 x = va[v];
+            const ulonglong2 y = (OP <= 1) ? vb[v] : x;
+            const int t = head + 2 * v;
+            ulonglong2 r;
+            r.x = row_op<OP>(x.x, y.x, s, t == L - 1);
+            r.y = row_op<OP>(x.y, y.y, s, t + 1 == L - 1);
+            vo[v] = r;
+        }
+        const int done = head + 2 * nvec;
+        if (tid == 0 && done < L) ro[done] = row_op<OP>(ra[done], rb[done], s, true);
+        return;
+    }
+    for (int t0 = tid; t0 < L; t0 += 4 * nthr) {
+        u64 x[4], y[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int t = t0 + u * nthr;
+            x[u] = (t < L) ? ra[t] : 0ULL;
+            y[u] = (OP <= 1 && t < L) ? rb[t] : 0ULL;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int t = t0 + u * nthr;
+            if (t < L) ro[t] = row_op<OP>(x[u], y[u], s, t == L - 1);
+        }
     }
 }
 
 // ---- general clear-weighted gather: out[e] = sum_j w[e][j] * x[idx[e][j]] (+ bias on body)
-// idx < 0 or w == 0 => no term (zero weights of ternary matrices are skipped warp-uniformly).
-// Covers dot / matmul / conv2d / sum in one kernel; grid = (E, column chunks), 4 columns/thread.
-#define GM_TPT 4
+// idx < 0 or w == 0 => no term: the taps of an output row are compacted into shared memory once per CTA (zero weights
+// of ternary matrices and padding cost nothing in the inner loop).  Covers dot / conv2d / sum and the matmuls the
+// tiled kernel does not take; grid = (E, column chunks), GM_TPT columns per thread, coalesced 8-byte accesses
+// (operand rows start on either 16-byte phase).  More than a few taps per output make this kernel INT-ALU bound
+// (3 IMAD per u64 multiply-add), not HBM bound: see DESIGN.md 4.3.
+#define GM_TPT 8
+#define GM_MAXTAPS 1024
 __global__ void __launch_bounds__(256)
 k_gather_mac(u64* __restrict__ out, const u64* __restrict__ x, const int* __restrict__ idx,
              const i64* __restrict__ w, const u64* __restrict__ bias, int K, int L) {
+    __shared__ int s_src[GM_MAXTAPS];
+    __shared__ i64 s_w[GM_MAXTAPS];
+    __shared__ int s_cnt;
     const long e = blockIdx.x;
     const int* ie = idx + (size_t)e * K;
     const i64* we = w + (size_t)e * K;
-    for (int t0 = blockIdx.y * blockDim.x * GM_TPT + threadIdx.x; t0 < L;
-         t0 += gridDim.y * blockDim.x * GM_TPT) {
-        u64 acc[GM_TPT];
+    const u64 be = bias ? bias[e] : 0ULL;
+    for (int k0 = 0; k0 < K; k0 += GM_MAXTAPS) {        // (K > GM_MAXTAPS: several rounds, accumulating into out)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int c = 0;
+            const int k1 = (K - k0 < GM_MAXTAPS) ? K - k0 : GM_MAXTAPS;
+            for (int j = 0; j < k1; j++) {
+                const int sidx = ie[k0 + j];
+                const i64 wj = we[k0 + j];
+                if (sidx >= 0 && wj != 0) { s_src[c] = sidx; s_w[c] = wj; c++; }
+            }
+            s_cnt = c;
+        }
+        __syncthreads();
+        const int cnt = s_cnt;
+        for (int t0 = blockIdx.y * blockDim.x * GM_TPT + threadIdx.x; t0 < L;
+             t0 += gridDim.y * blockDim.x * GM_TPT) {
+            u64 acc[GM_TPT];
 #pragma unroll
-        for (int u = 0; u < GM_TPT; u++) acc[u] = 0;
-        for (int j = 0; j < K; j++) {
-            const int s = __ldg(ie + j);
-            const u64 wj = (u64)__ldg(we + j);
-            if (s < 0 || wj == 0) continue;
-            const u64* src = x + (size_t)s * L;
+            for (int u = 0; u < GM_TPT; u++) acc[u] = 0;
+            for (int j = 0; j < cnt; j++) {
+                const u64 wj = (u64)s_w[j];
+                const u64* src = x + (size_t)s_src[j] * L;
+#pragma unroll
+                for (int u = 0; u < GM_TPT; u++) {
+                    const int t = t0 + u * blockDim.x;
+                    if (t < L) acc[u] += wj * src[t];
+                }
+            }
 #pragma unroll
             for (int u = 0; u < GM_TPT; u++) {
-                int t = t0 + u * blockDim.x;
-                if (t < L) acc[u] += wj * src[t];
+                const int t = t0 + u * blockDim.x;
+                if (t < L) {
+                    u64* o = out + (size_t)e * L + t;
+                    if (k0 == 0) *o = acc[u] + ((t == L - 1) ? be : 0ULL);
+                    else *o += acc[u];
+                }
             }
-        }
-#pragma unroll
-        for (int u = 0; u < GM_TPT; u++) {
-            int t = t0 + u * blockDim.x;
-            if (t < L) out[(size_t)e * L + t] = acc[u] + ((bias && t == L - 1) ? bias[e] : 0ULL);
         }
     }
 }
@@ -100,8 +164,9 @@ k_gather_mac(u64* __restrict__ out, const u64* __restrict__ x, const int* __rest
 #define MM_TN 16
 __global__ void __launch_bounds__(256)
 k_matmul(u64* __restrict__ out, const u64* __restrict__ x, const i64* __restrict__ W, int K, int Nc,
-         int L) {
+         int L, const int* __restrict__ skip_if_set) {
     extern __shared__ i64 s_w[];   // [K][MM_TN]
+    if (skip_if_set && *skip_if_set) return;          // the staged kernel took this matmul
     const long m = blockIdx.x;
     const int n0 = blockIdx.y * MM_TN;
     for (int t = threadIdx.x; t < K * MM_TN; t += blockDim.x) {
@@ -126,9 +191,71 @@ k_matmul(u64* __restrict__ out, const u64* __restrict__ x, const i64* __restrict
     }
 }
 
+// ---- matmul with the operand tile staged in shared memory: x is read from HBM exactly ONCE.
+// CTA (m, chunk of MS_TC words): x[m][0..K)[chunk] -> shared memory (K x 512 B), the non-zero weights of every output
+// column n compacted to (k, w) lists (ternary / sparse weight matrices cost only their non-zeros), then every
+// (n, word) output is a short sum over its list read from shared memory.  Algorithmic bytes = traffic:
+// (Mr*K + Mr*Nc)*L*8.  Requires int32 weights and K*MS_TC*8 + Nc*K*6 + Nc*4 bytes of shared memory.
+#define MS_TC 64
+__global__ void __launch_bounds__(256)
+k_matmul_staged(u64* __restrict__ out, const u64* __restrict__ x, const i64* __restrict__ W, int K, int Nc, int L,
+                const int* __restrict__ run_if_set) {
+    extern __shared__ __align__(16) unsigned char ms_raw[];
+    if (!*run_if_set) return;                          // some weight needs more than 32 bits: the dense kernel runs
+    u64* xt = reinterpret_cast<u64*>(ms_raw);                              // [K][MS_TC]
+    int* ww = reinterpret_cast<int*>(xt + (size_t)K * MS_TC);              // [Nc][K] weights of the kept taps
+    int* cnt = ww + (size_t)Nc * K;                                         // [Nc]
+    unsigned short* kk = reinterpret_cast<unsigned short*>(cnt + Nc);       // [Nc][K] their k
+    const long m = blockIdx.x;
+    const int t0 = blockIdx.y * MS_TC;
+    const u64* xm = x + (size_t)m * K * L;
+    for (int i = threadIdx.x; i < K * MS_TC; i += blockDim.x) {
+        const int k = i / MS_TC, c = i - k * MS_TC;
+        xt[i] = (t0 + c < L) ? xm[(size_t)k * L + t0 + c] : 0ULL;
+    }
+    for (int n = threadIdx.x; n < Nc; n += blockDim.x) {
+        int c = 0;
+        for (int k = 0; k < K; k++) {
+            const i64 wv = W[(size_t)k * Nc + n];
+            if (wv != 0) { kk[(size_t)n * K + c] = (unsigned short)k; ww[(size_t)n * K + c] = (int)wv; c++; }
+        }
+        cnt[n] = c;
+    }
+    __syncthreads();
+    const int c = threadIdx.x & (MS_TC - 1);
+    if (t0 + c >= L) return;
+    for (int n = threadIdx.x / MS_TC; n < Nc; n += blockDim.x / MS_TC) {
+        const int cn = cnt[n];
+        const unsigned short* kn = kk + (size_t)n * K;
+        const int* wn = ww + (size_t)n * K;
+        u64 acc = 0;
+        for (int j = 0; j < cn; j++) acc += (u64)(i64)wn[j] * xt[(int)kn[j] * MS_TC + c];
+        out[((size_t)m * Nc + n) * L + t0 + c] = acc;
+    }
+}
+
+static int g_sm_count = 0;
+static inline int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            g_sm_count = sms;
+        else
+            g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
 static inline int col_chunks(int L, int per_block) {
     int c = (L + per_block - 1) / per_block;
     return c < 1 ? 1 : (c > 64 ? 64 : c);
+}
+
+// do all weights fit a signed 32-bit integer?  Decided ON DEVICE (no host synchronisation inside Server.run): flag
+// stays 1 unless some weight does not fit; both matmul kernels are enqueued and the one the flag rules out exits at once.
+__global__ void k_weights_fit(const i64* __restrict__ W, long n, int* flag) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        if (W[i] != (i64)(int)W[i]) *flag = 0;
 }
 
 extern "C" {
@@ -144,10 +271,11 @@ int fhe_lin_add(u64* out, const u64* a, const u64* b, const int* ia, const int* 
     cudaStream_t st = (cudaStream_t)stream;
     if (!ia && !ib && LIN_ALIGNED16(out, a, b)) {
         long words = E * (long)L;
-        int grid = (int)((words / 2 + 255) / 256 < 148L * 8 ? (words / 2 + 255) / 256 : 148L * 8);
+        const long cap = (long)sm_count() * 8;
+        int grid = (int)((words / 2 + 255) / 256 < cap ? (words / 2 + 255) / 256 : cap);
         k_flat<0><<<grid < 1 ? 1 : grid, 256, 0, st>>>(out, a, b, words);
     } else
-        k_rows<0><<<dim3((unsigned)E, col_chunks(L, 1024)), 256, 0, st>>>(out, a, b, ia, ib, nullptr, L);
+        k_rows<0><<<dim3((unsigned)E, col_chunks(L, 2048)), 256, 0, st>>>(out, a, b, ia, ib, nullptr, L);
     FHE_CHECK_LAUNCH();
     return 0;
 }
@@ -158,10 +286,11 @@ int fhe_lin_sub(u64* out, const u64* a, const u64* b, const int* ia, const int* 
     cudaStream_t st = (cudaStream_t)stream;
     if (!ia && !ib && LIN_ALIGNED16(out, a, b)) {
         long words = E * (long)L;
-        int grid = (int)((words / 2 + 255) / 256 < 148L * 8 ? (words / 2 + 255) / 256 : 148L * 8);
+        const long cap = (long)sm_count() * 8;
+        int grid = (int)((words / 2 + 255) / 256 < cap ? (words / 2 + 255) / 256 : cap);
         k_flat<1><<<grid < 1 ? 1 : grid, 256, 0, st>>>(out, a, b, words);
     } else
-        k_rows<1><<<dim3((unsigned)E, col_chunks(L, 1024)), 256, 0, st>>>(out, a, b, ia, ib, nullptr, L);
+        k_rows<1><<<dim3((unsigned)E, col_chunks(L, 2048)), 256, 0, st>>>(out, a, b, ia, ib, nullptr, L);
     FHE_CHECK_LAUNCH();
     return 0;
 }
@@ -172,10 +301,11 @@ int fhe_lin_neg(u64* out, const u64* a, const int* ia, long E, int L, void* stre
     cudaStream_t st = (cudaStream_t)stream;
     if (!ia && LIN_ALIGNED16(out, a, a)) {
         long words = E * (long)L;
-        int grid = (int)((words / 2 + 255) / 256 < 148L * 8 ? (words / 2 + 255) / 256 : 148L * 8);
+        const long cap = (long)sm_count() * 8;
+        int grid = (int)((words / 2 + 255) / 256 < cap ? (words / 2 + 255) / 256 : cap);
         k_flat<2><<<grid < 1 ? 1 : grid, 256, 0, st>>>(out, a, nullptr, words);
     } else
-        k_rows<2><<<dim3((unsigned)E, col_chunks(L, 1024)), 256, 0, st>>>(out, a, nullptr, ia, nullptr, nullptr, L);
+        k_rows<2><<<dim3((unsigned)E, col_chunks(L, 2048)), 256, 0, st>>>(out, a, nullptr, ia, nullptr, nullptr, L);
     FHE_CHECK_LAUNCH();
     return 0;
 }
@@ -184,7 +314,7 @@ int fhe_lin_neg(u64* out, const u64* a, const int* ia, long E, int L, void* stre
 int fhe_lin_add_plain(u64* out, const u64* a, const int* ia, const u64* pt, long E, int L, void* stream) {
     if (!LIN_ARGS_OK(E, L)) FHE_FAIL(2, "lin_add_plain: bad arguments");
     if (E == 0) return 0;
-    k_rows<3><<<dim3((unsigned)E, col_chunks(L, 1024)), 256, 0, (cudaStream_t)stream>>>(out, a, nullptr, ia, nullptr, pt, L);
+    k_rows<3><<<dim3((unsigned)E, col_chunks(L, 2048)), 256, 0, (cudaStream_t)stream>>>(out, a, nullptr, ia, nullptr, pt, L);
     FHE_CHECK_LAUNCH();
     return 0;
 }
@@ -193,7 +323,7 @@ int fhe_lin_add_plain(u64* out, const u64* a, const int* ia, const u64* pt, long
 int fhe_lin_plain_sub(u64* out, const u64* a, const int* ia, const u64* pt, long E, int L, void* stream) {
     if (!LIN_ARGS_OK(E, L)) FHE_FAIL(2, "lin_plain_sub: bad arguments");
     if (E == 0) return 0;
-    k_rows<5><<<dim3((unsigned)E, col_chunks(L, 1024)), 256, 0, (cudaStream_t)stream>>>(out, a, nullptr, ia, nullptr, pt, L);
+    k_rows<5><<<dim3((unsigned)E, col_chunks(L, 2048)), 256, 0, (cudaStream_t)stream>>>(out, a, nullptr, ia, nullptr, pt, L);
     FHE_CHECK_LAUNCH();
     return 0;
 }
@@ -202,7 +332,7 @@ int fhe_lin_plain_sub(u64* out, const u64* a, const int* ia, const u64* pt, long
 int fhe_lin_mul_clear(u64* out, const u64* a, const int* ia, const i64* c, long E, int L, void* stream) {
     if (!LIN_ARGS_OK(E, L)) FHE_FAIL(2, "lin_mul_clear: bad arguments");
     if (E == 0) return 0;
-    k_rows<4><<<dim3((unsigned)E, col_chunks(L, 1024)), 256, 0, (cudaStream_t)stream>>>(
+    k_rows<4><<<dim3((unsigned)E, col_chunks(L, 2048)), 256, 0, (cudaStream_t)stream>>>(
         out, a, nullptr, ia, nullptr, reinterpret_cast<const u64*>(c), L);
     FHE_CHECK_LAUNCH();
     return 0;
@@ -222,11 +352,34 @@ int fhe_lin_gather_mac(u64* out, const u64* x, const int* idx, const i64* w, con
 int fhe_matmul_ct_clear(u64* out, const u64* x, const i64* W, long Mr, int K, int Nc, int L, void* stream) {
     if (Mr < 0 || K <= 0 || Nc <= 0 || L <= 0) FHE_FAIL(2, "matmul_ct_clear: bad arguments");
     if (Mr == 0) return 0;
-    size_t smem = (size_t)K * MM_TN * sizeof(i64);
-    if (smem > 48 * 1024) FHE_FAIL(3, "matmul_ct_clear: K=%d too large for the tiled kernel (use gather_mac)", K);
-    dim3 grid((unsigned)Mr, (Nc + MM_TN - 1) / MM_TN, col_chunks(L, 256));
-    k_matmul<<<grid, 256, smem, (cudaStream_t)stream>>>(out, x, W, K, Nc, L);
-    FHE_CHECK_LAUNCH();
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem_dense = (size_t)K * MM_TN * sizeof(i64);
+    const size_t smem_staged = (size_t)K * MS_TC * 8 + (size_t)Nc * K * 6 + (size_t)Nc * 4 + 16;
+    const bool staged_ok = K <= 65535 && smem_staged <= 200 * 1024;
+    const bool dense_ok = smem_dense <= 48 * 1024;
+    if (!staged_ok && !dense_ok) FHE_FAIL(3, "matmul_ct_clear: K=%d too large for the tiled kernels (use gather_mac)", K);
+    int* d_flag = nullptr;
+    if (staged_ok) {
+        // staged kernel (x read once, sparse weights cost their non-zeros) when every weight fits 32 bits
+        FHE_CUDA(cudaMallocAsync(&d_flag, sizeof(int), st));
+        FHE_CUDA(cudaMemsetAsync(d_flag, 1, sizeof(int), st));          // non-zero = "staged kernel runs"
+        if (dense_ok) {
+            const long n = (long)K * Nc;
+            k_weights_fit<<<(unsigned)((n + 255) / 256 < 64 ? (n + 255) / 256 : 64), 256, 0, st>>>(W, n, d_flag);
+        }
+        // (no dense fallback for this K: the staged kernel must run; weights would be truncated to 32 bits only if the
+        // caller handed over wider ones, which FHE circuits -- clear ints of at most 17 bits -- never do)
+        FHE_CUDA(cudaFuncSetAttribute(k_matmul_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
+        dim3 grid((unsigned)Mr, (unsigned)((L + MS_TC - 1) / MS_TC));
+        k_matmul_staged<<<grid, 256, smem_staged, st>>>(out, x, W, K, Nc, L, d_flag);
+        FHE_CHECK_LAUNCH();
+    }
+    if (dense_ok) {
+        dim3 grid((unsigned)Mr, (Nc + MM_TN - 1) / MM_TN, col_chunks(L, 256));
+        k_matmul<<<grid, 256, smem_dense, st>>>(out, x, W, K, Nc, L, d_flag);
+        FHE_CHECK_LAUNCH();
+    }
+    if (d_flag) FHE_CUDA(cudaFreeAsync(d_flag, st));
     return 0;
 }
 

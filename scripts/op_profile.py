@@ -1,36 +1,90 @@
-"""Development aid: per-op-type device+host time of one circuit run (synchronising after every op)."""
-import os, sys, time, collections
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+"""HBM roofline of the torus linear kernels at the BASELINE shapes (SURVEY 8d algorithmic bytes / CUDA-event time /
+measured HBM copy bandwidth of MEASURED_PEAKS.json).  Writes gpurun_out/op_profile.json.
+usage: op_profile.py [reps]            (ncu target: op_profile.py 1)"""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
-from concrete_numpy_b200 import api, executor as X
-from golden_util import load_golden, to_value
-name = sys.argv[1] if len(sys.argv) > 1 else "cfg5_kvdb128_insert"
-doc = load_golden(name)
-circuit = api.Circuit(doc["mlir"], doc["input_signs"], doc["output_signs"], api.Configuration(jit=True, global_p_error=doc["global_p_error"]))
-args = [to_value(a) for a in doc["cases"][0]["args"]]
-circuit.keygen()
-enc = circuit.encrypt(*args)
-ev = circuit.client.evaluation_keys
-circuit.server.run(enc, ev)
-acc = collections.defaultdict(lambda: [0, 0.0, 0])
-orig_init = X.Executor.run
-def timed_run(self, evk, a):
-    for k, h in list(self.handlers.items()):
-        def mk(k=k, h=h):
-            def w(op, v):
-                torch.cuda.synchronize(); t0 = time.perf_counter()
-                r = h(op, v)
-                torch.cuda.synchronize(); dt = time.perf_counter() - t0
-                acc[k][0] += 1; acc[k][1] += dt; acc[k][2] += (op.result_type.size if hasattr(op.result_type, "size") else 0)
-                return r
-            return w
-        self.handlers[k] = mk()
-    return orig_init(self, evk, a)
-X.Executor.run = timed_run
-torch.cuda.synchronize(); t0 = time.perf_counter()
-circuit.server.run(enc, ev)
-torch.cuda.synchronize(); total = time.perf_counter() - t0
-print(name, "total %.1f ms" % (total * 1e3))
-for k, (n, t, sz) in sorted(acc.items(), key=lambda kv: -kv[1][1]):
-    print(f"  {k:28s} calls {n:5d}  {t*1e3:9.2f} ms  ({t/n*1e6:8.1f} us/call, {sz} result elems)")
+from concrete_numpy_b200 import engine as E
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+dev = torch.device("cuda:0")
+try:
+    HBM = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:                                                       # noqa: BLE001
+    HBM = 6650.0
+rng = np.random.default_rng(0)
+res = {"hbm_gbs_peak": HBM}
+
+
+def timed(fn):
+    fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev); flush.zero_()      # > L2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def report(name, ms, nbytes, note=""):
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    res[name] = {"ms": round(ms, 4), "algorithmic_bytes": int(nbytes), "gbs": round(gbs, 1), "frac_of_hbm": round(gbs / HBM, 3), "note": note}
+    print(name, json.dumps(res[name]), flush=True)
+
+
+def rand_ct(rows, L):
+    return torch.randint(-(1 << 62), 1 << 62, (rows, L), dtype=torch.int64, device=dev)
+
+
+# cfg3: x [64,128] @ W [128,64] ternary (10 non-zeros per column), N = 8192
+L = 8193
+x = rand_ct(64 * 128, L)
+W = np.zeros((128, 64), dtype=np.int64)
+for n in range(64):
+    W[rng.choice(128, 10, replace=False), n] = rng.choice([-1, 1], 10)
+Wd = torch.from_numpy(W).to(dev)
+report("cfg3_matmul_64x128x64_sparse_ternary", timed(lambda: E.matmul_ct_clear(x, Wd, 64, 128, 64, L)),
+       (64 * 128 + 64 * 64) * L * 8 + 128 * 64 * 8, "staged kernel, 10 non-zero weights per column")
+Wfull = torch.from_numpy(rng.integers(-3, 4, (128, 64)).astype(np.int64)).to(dev)
+report("matmul_64x128x64_dense_weights", timed(lambda: E.matmul_ct_clear(x, Wfull, 64, 128, 64, L)),
+       (64 * 128 + 64 * 64) * L * 8 + 128 * 64 * 8, "same shape, dense weights: 4.3e9 u64 MACs -> INT-ALU bound")
+del x
+# cfg4: conv2d 1x8x28x28, 3x3, pad 1 (72 taps per output) through gather-MAC
+xin = rand_ct(8 * 28 * 28, L)
+idx = np.full((8, 28, 28, 72), -1, dtype=np.int32)
+w = np.zeros((8, 28, 28, 72), dtype=np.int64)
+Wc = rng.integers(-1, 2, (8, 8, 3, 3))
+for f in range(8):
+    for c in range(8):
+        for kh in range(3):
+            for kw in range(3):
+                kk = (c * 3 + kh) * 3 + kw
+                for oh in range(28):
+                    ih = oh - 1 + kh
+                    if not 0 <= ih < 28:
+                        continue
+                    for ow in range(28):
+                        iw = ow - 1 + kw
+                        if 0 <= iw < 28:
+                            idx[f, oh, ow, kk] = (c * 28 + ih) * 28 + iw
+                            w[f, oh, ow, kk] = Wc[f, c, kh, kw]
+di, dw = torch.from_numpy(idx.reshape(-1, 72)).to(dev), torch.from_numpy(w.reshape(-1, 72)).to(dev)
+report("cfg4_conv2d_8x28x28_3x3_gather_mac", timed(lambda: E.lin_gather_mac(xin, di, dw, L)), 2 * 6272 * L * 8,
+       f"{int((w != 0).sum())} u64 MACs x {L} words: INT-ALU bound")
+# elementwise at the cfg2 shape (4096 ciphertexts of N = 32768): add, add-plain, mul-clear, neg
+L2 = 32769
+a, b = rand_ct(4096, L2), rand_ct(4096, L2)
+report("add_eint_4096x32769_flat", timed(lambda: E.lin_add(a, b, L2)), 3 * 4096 * L2 * 8)
+ident = torch.arange(4096, dtype=torch.int32, device=dev)
+report("add_eint_4096x32769_row_mapped", timed(lambda: E.lin_add(a, b, L2, ident, ident, 4096)), 3 * 4096 * L2 * 8)
+pt = torch.randint(0, 1 << 62, (4096,), dtype=torch.int64, device=dev)
+report("add_eint_int_4096x32769", timed(lambda: E.lin_add_plain(a, pt, L2)), 2 * 4096 * L2 * 8)
+report("mul_eint_int_4096x32769", timed(lambda: E.lin_mul_clear(a, pt, L2)), 2 * 4096 * L2 * 8)
+report("neg_eint_4096x32769", timed(lambda: E.lin_neg(a, L2)), 2 * 4096 * L2 * 8)
+rev = torch.arange(4095, -1, -1, dtype=torch.int32, device=dev)
+report("add_eint_4096x32769_reversed_rows", timed(lambda: E.lin_add(a, b, L2, rev, ident, 4096)), 3 * 4096 * L2 * 8,
+       "operand rows on the other 16-byte phase: 8-byte accesses")
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(res, open("gpurun_out/op_profile.json", "w"), indent=1)

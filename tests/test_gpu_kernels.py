@@ -302,6 +302,55 @@ def test_linear_ops_bit_exact(oracle, cuda_device):
     assert np.array_equal(E.to_np_u64(got), oracle.lin_gather_mac(x, gi, gw))
 
 
+@pytest.mark.parametrize("L", [1, 2, 513, 2049])
+def test_linear_kernels_all_paths_bit_exact(oracle, cuda_device, L):
+    """Every code path of the round-2 linear kernels: rows on both 16-byte phases (vector path with scalar head / tail,
+    scalar path when operand rows differ in phase), the staged matmul (x read once, sparse weights compacted) and its
+    dense fallback for weights beyond 32 bits, gather-MAC with more taps than one shared-memory round holds."""
+    rng = np.random.default_rng(L)
+    Erows = 11
+    a = rng.integers(0, 1 << 64, (Erows, L), dtype=np.uint64)
+    b = rng.integers(0, 1 << 64, (Erows, L), dtype=np.uint64)
+    da, db = E.from_np_u64(a, cuda_device), E.from_np_u64(b, cuda_device)
+    for ia_np, ib_np in [(np.arange(Erows), np.arange(Erows)),              # same phase everywhere: vector path
+                         (np.arange(Erows)[::-1].copy(), np.arange(Erows)),  # reversed rows: phases agree only for odd counts
+                         (rng.integers(0, Erows, Erows), rng.integers(0, Erows, Erows))]:
+        ia = torch.from_numpy(ia_np.astype(np.int32)).to(cuda_device)
+        ib = torch.from_numpy(ib_np.astype(np.int32)).to(cuda_device)
+        assert np.array_equal(E.to_np_u64(E.lin_add(da, db, L, ia, ib, E=Erows)), a[ia_np] + b[ib_np])
+        assert np.array_equal(E.to_np_u64(E.lin_sub(da, db, L, ia, ib, E=Erows)), a[ia_np] - b[ib_np])
+        pt = rng.integers(0, 1 << 64, Erows, dtype=np.uint64)
+        exp = a[ia_np].copy()
+        exp[:, -1] += pt
+        assert np.array_equal(E.to_np_u64(E.lin_add_plain(da, E.from_np_u64(pt, cuda_device), L, ia)), exp)
+        exp = np.uint64(0) - a[ia_np]
+        exp[:, -1] += pt
+        assert np.array_equal(E.to_np_u64(E.lin_plain_sub(da, E.from_np_u64(pt, cuda_device), L, ia)), exp)
+        c = rng.integers(-(1 << 40), 1 << 40, Erows).astype(np.int64)
+        assert np.array_equal(E.to_np_u64(E.lin_mul_clear(da, torch.from_numpy(c).to(cuda_device), L, ia)),
+                              a[ia_np] * c.view(np.uint64)[:, None])
+    # matmul: sparse ternary weights (staged kernel), dense small weights, and 40-bit weights (dense fallback)
+    for Mr, K, Nc, wgen in [(3, 128, 64, lambda: rng.choice([-1, 0, 0, 0, 0, 0, 0, 1], (128, 64))),
+                            (4, 5, 3, lambda: rng.integers(-9, 10, (5, 3))),
+                            (2, 6, 17, lambda: rng.integers(-(1 << 40), 1 << 40, (6, 17)))]:
+        x = rng.integers(0, 1 << 64, (Mr * K, L), dtype=np.uint64)
+        W = wgen().astype(np.int64)
+        got = E.matmul_ct_clear(E.from_np_u64(x, cuda_device), torch.from_numpy(W).to(cuda_device), Mr, K, Nc, L)
+        exp = np.zeros((Mr, Nc, L), dtype=np.uint64)
+        xr = x.reshape(Mr, K, L)
+        for kk in range(K):
+            exp += W[kk].view(np.uint64)[None, :, None] * xr[:, kk][:, None, :]
+        assert np.array_equal(E.to_np_u64(got), exp.reshape(Mr * Nc, L)), (Mr, K, Nc)
+    # gather-MAC with 1500 taps per output (two shared-memory rounds), zero weights and "no term" entries
+    Kt = 1500
+    idx = rng.integers(-1, Erows, (3, Kt)).astype(np.int32)
+    w = rng.integers(-2, 3, (3, Kt)).astype(np.int64)
+    bias = rng.integers(0, 1 << 64, 3, dtype=np.uint64)
+    got = E.lin_gather_mac(da, torch.from_numpy(idx).to(cuda_device), torch.from_numpy(w).to(cuda_device), L,
+                           E.from_np_u64(bias, cuda_device))
+    assert np.array_equal(E.to_np_u64(got), oracle.lin_gather_mac(a, idx, w, bias))
+
+
 def test_linear_ops_on_misaligned_row_slices(oracle, cuda_device):
     """Row slices of [E, L] tensors with odd L start 8 bytes off a 16-byte boundary: the flat vectorised path
     must not be taken for them (the CRT lanes of the wide path hand such slices around)."""
