@@ -17,7 +17,7 @@ def _log2_std(err_u64):
     return math.log2(err_u64.view(np.int64).astype(np.float64).std() / 2.0 ** 64 + 1e-300)
 
 
-@pytest.mark.parametrize("bits,B,oracle_n", [(4, 2048, 256), (6, 256, 8)])
+@pytest.mark.parametrize("bits,B,oracle_n", [(4, 2048, 256), (6, 256, 8), (8, 64, 16)])   # 8: the set the bench times
 def test_bootstrap_noise_vs_oracle_and_model(oracle, cuda_device, bits, B, oracle_n):
     p = P.REFERENCE_SETS[bits]
     ks = E.KeySet(p, cuda_device, seed=3, keep_std_bsk=True)
