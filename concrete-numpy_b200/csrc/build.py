@@ -17,7 +17,7 @@ def needs_build() -> bool:
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = SOURCES + ["common.cuh", "pbs_kernels.cuh", "tmem.cuh", "build.py"]
+    deps = SOURCES + ["common.cuh", "pbs_kernels.cuh", "pbs_pipe.cuh", "tmem.cuh", "build.py"]
     return any(os.path.getmtime(os.path.join(HERE, s)) > t for s in deps)
 
 

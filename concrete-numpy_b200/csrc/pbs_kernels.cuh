@@ -79,6 +79,9 @@ struct PbsPlan {
     // the next CMUX instead: every update is pushed (st.shared::cluster, fire and forget) to the CTA that will need
     // it as X^a * ACC.  The latency-bound remote loads of P1 become posted stores that drain behind P5.
     static constexpr bool ACC_TM = (ACCTM_ != 0);
+    // PIPE (ACCTM_ == 2): k = 1 / two-level bootstraps of this plan run k_pbs_pipe (pbs_pipe.cuh): bulk-copied forward
+    // exchange from local staging buffers, one mbarrier per buffer instead of cluster-wide barriers
+    static constexpr bool PIPE = (ACCTM_ == 2);
     static constexpr int ACC_ITEMS = ACC_TM ? (2 << (LOGL1 - LOGC)) / NT_ : 0;     // (k+1)*Q / NT items per thread
     static constexpr int TM_ACC = ACC_TM ? ACC_ITEMS * 4 * (1 << LOGR1_) : 0;      // 2*R1 u64 per item
     static constexpr int TM_THREAD = TM_A + TM_B + TM_ACC;
@@ -368,7 +371,8 @@ __device__ __forceinline__ void tw_teardown(const TwCtx& tw) {
 // A thread keeps the R-1 twiddles of its butterfly index in registers across the buffers it handles.
 template <int LR, int LOGLC, int LOGBUF, int NT, bool INV, bool TM>
 __device__ __forceinline__ void mid_pass(double2* __restrict__ work, int nbuf, unsigned tw_taddr /* TMEM */,
-                                         const double2* __restrict__ tw /* shared: [(R-1)][S] */) {
+                                         const double2* __restrict__ tw /* shared: [(R-1)][S] */,
+                                         int bstep = 1 /* distance between the buffers, in buffers */) {
     constexpr int R = 1 << LR;
     constexpr int LOGSS = LOGLC - LR, SS = 1 << LOGSS;          // stride inside a sub-transform
     constexpr int NBF = 1 << (LOGBUF - LR);                     // butterflies per buffer
@@ -394,7 +398,7 @@ __device__ __forceinline__ void mid_pass(double2* __restrict__ work, int nbuf, u
             tmem_load_c<TMW / 4>(tw_taddr, t + 1);
 #pragma unroll 1
         for (int buf = grp; buf < nbuf; buf += GROUPS) {
-            double2* base = work + ((size_t)buf << LOGBUF);
+            double2* base = work + ((size_t)(buf * bstep) << LOGBUF);
             double2 x[R];
 #pragma unroll
             for (int r = 0; r < R; r++) x[r] = base[SW(pos0 + (r << LOGSS))];
@@ -1213,6 +1217,8 @@ k_cmux(u64* __restrict__ out, const u64* __restrict__ pool, const int* __restric
     tw_teardown<P>(tw);
 }
 
+#include "pbs_pipe.cuh"
+
 // ------------------------------------------------------------------ host launch helpers ----
 template <typename Kern, typename... Args>
 static int launch_clustered(Kern kern, int C, int NT, int tmem_cols, size_t smem, long work_items, cudaStream_t st,
@@ -1306,7 +1312,16 @@ struct PbsPlanOps {
         if (per_sm > 512 / P::TM_CTA) per_sm = 512 / P::TM_CTA;
         return per_sm * sms;
     }
+    static size_t smem_pipe() { return (size_t)2 * P::S * 8 + (size_t)5 * P::BUF * 16; }
     static int pbs(const PbsLaunchArgs& a) {
+        if constexpr (P::PIPE) {
+            // development knob, read once: FHE_PBS_PIPE=0 runs the plan's generic kernel (A/B measurements)
+            static const bool use_pipe = [] { const char* e = getenv("FHE_PBS_PIPE"); return !(e && e[0] == '0'); }();
+            const bool plain = !(a.bsk_ct_stride || a.g.nout > 1 || a.g.theta > 0);
+            if (use_pipe && plain && a.g.k == 1 && a.g.level == 2 && 2 * a.g.base_log <= 30 && a.g.base_log >= 2)
+                return launch_clustered(k_pbs_pipe<P>, P::C, P::NT, P::TM_CTA, smem_pipe(), a.B, a.st, a.out, a.in, a.B,
+                                        a.bskF, a.luts, a.lut_idx, a.g, a.twT, a.tw_mid, a.prof);
+        }
         if (a.bsk_ct_stride || a.g.nout > 1 || a.g.theta > 0)
             return launch_clustered(k_pbs<P, true>, P::C, P::NT, P::TM_CTA, smem_pbs(a.g), a.B, a.st, a.out, a.in, a.B,
                                     a.bskF, a.luts, a.lut_idx, a.g, a.twT, a.tw_mid, a.prof, a.bsk_ct_stride);

@@ -1,0 +1,380 @@
+// Pipelined bootstrap for the large cluster plans (N = 32768 on 8 CTAs, k = 1, two decomposition levels).
+//
+// Same arithmetic, same Fourier key layout and same FFT factorisation as k_pbs with the accumulator in tensor memory
+// (PbsPlan::ACC_TM); what changes is how the three exchanges of a CMUX cross the cluster:
+//
+//   * forward (stage-1 outputs, 112 KiB per CTA and CMUX): every thread writes its R1 outputs into a LOCAL staging
+//     buffer ordered by destination CTA; 4 KiB chunks then travel as bulk asynchronous copies
+//     (cp.async.bulk.shared::cluster, ~2-3x the rate of element-wise st.shared::cluster under load,
+//     profiles/r01_ubench_dsmem_bulk.log) and complete on one mbarrier per work buffer in the destination CTA.  The
+//     copy engine moves polynomial 0 while the threads decompose polynomial 1, and polynomial 1 while they run the
+//     mid passes of polynomial 0.  Staging space: one spare 32 KiB buffer plus the two halves of the rotated-accumulator
+//     array, each dead as soon as its polynomial has been read.
+//   * inverse: bulk copies into the peers' spare work buffers, one mbarrier per output polynomial (as in k_pbs).
+//   * rotated accumulator of the next CMUX: st.async (remote store + complete_tx) counted on one mbarrier per
+//     polynomial in the destination, so the next CMUX starts on polynomial 0 while polynomial 1 still drains.
+//
+// No cluster-wide release/acquire barrier (MEMBAR.ALL.GPU + drain) is left inside a CMUX: a CTA waits only for the
+// bytes it is about to read.  The hardware cluster barrier is used twice per CMUX in its relaxed split form
+// (arrive early, wait late): "staging buffer X has been read by every destination" and "my spare buffers are free".
+//
+// Buffer map (level = 2): digit polynomial (c, lv) lives in work buffer 2*lv + c.  The buffers polynomial 0 is sent to
+// (0 and 2) are exactly the ones whose previous contents -- output 0 and the inverse exchange of output 0 -- are known
+// to be consumed once the rotated polynomial 0 of the next CMUX has arrived from every CTA; likewise 1 and 3.
+//
+// Replaces memref_batched_bootstrap_lwe_u64 of the absent concrete-compiler runtime
+// (concrete/numpy/compilation/server.py:286, concrete/numpy/mlir/node_converter.py:1129-1208).
+#pragma once
+
+__device__ __forceinline__ void st_async_u64(unsigned dst_cluster_addr, u64 v, unsigned mbar_cluster_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(dst_cluster_addr), "l"(v), "r"(mbar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32-bit decomposition states of the 2*R1 coefficients of this thread's item of one polynomial:
+// closest representable of (X^a * ACC - ACC); the rotated operand was pushed into `rac` by its producers,
+// the thread's own words wait in its tensor-memory lane
+template <class P>
+__device__ __forceinline__ void pipe_read_state(const u64* __restrict__ rac, unsigned tacc, int q, int nonrep,
+                                                unsigned* st) {
+    constexpr int R1 = P::R1;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        unsigned ow[2 * R1];
+        u64 rv[R1];
+        TmemIo<2 * R1>::ld(tacc + (unsigned)(half * 2 * R1), ow);
+#pragma unroll
+        for (int e = 0; e < R1; e++) rv[e] = rac[((half * R1 + e) << P::LOGQ) + q];
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < R1; e++) {
+            const u64 diff = rv[e] - (((u64)ow[2 * e + 1] << 32) | (u64)ow[2 * e]);
+            const unsigned top = (unsigned)(diff >> 32);
+            st[half * R1 + e] = ((top >> (unsigned)(nonrep - 33)) + 1u) >> 1;
+        }
+    }
+}
+
+// next digit of every state (least significant level first), fold + twist, radix-R1 butterfly, stage twiddle
+template <class P>
+__device__ __forceinline__ void pipe_emit_compute(unsigned* st, int base_log, const double2* T, const PbsGeom& g,
+                                                  double2* v) {
+    constexpr int R1 = P::R1;
+    const unsigned mask = (1u << base_log) - 1u;
+    double2 z[R1];
+#pragma unroll
+    for (int j1 = 0; j1 < R1; j1++) {
+        double d[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int hj = h * R1 + j1;
+            const unsigned res = st[hj] & mask;
+            const unsigned s2 = st[hj] >> base_log;
+            const unsigned carry = (((res - 1u) | s2) & res) >> (base_log - 1);
+            st[hj] = s2 + carry;
+            d[h] = i32_to_f64((int)res - (int)(carry << base_log));
+        }
+        const double2 dd = make_double2(d[0], d[1]);
+        z[j1] = (j1 == 0) ? dd : cmul(dd, g.cj[j1]);
+    }
+    Dft<R1, false>::run(z);
+#pragma unroll
+    for (int t1 = 0; t1 < R1; t1++) v[t1] = cmul(z[t1], T[t1]);
+}
+
+// chunk t1 of the staging buffer goes to CTA t1; inside the chunk the element sits where the receiver's swizzle wants it
+template <class P>
+__device__ __forceinline__ void pipe_stage(double2* __restrict__ stg, int off, const double2* v) {
+#pragma unroll
+    for (int t1 = 0; t1 < P::R1; t1++) stg[(t1 << P::LOGQ) + off] = v[t1];
+}
+
+// thread d < C: chunk d of `stg` -> chunk `rank` of work buffer `dst_buf` of CTA d, counted on its mbarrier `bar`
+template <class P>
+__device__ __forceinline__ void pipe_send(const double2* stg, double2* dst_buf, u64* bar, int rank, int d) {
+    bulk_copy_to_cluster(mapa_u32(smem_u32(dst_buf + (rank << P::LOGQ)), d), stg + (d << P::LOGQ),
+                         (unsigned)(sizeof(double2) << P::LOGQ), mapa_u32(smem_u32(bar), d));
+}
+
+template <class P>
+__global__ void __launch_bounds__(P::NT, 1)
+k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* __restrict__ bskF,
+           const u64* __restrict__ luts, const int* __restrict__ lut_idx, const PbsGeom g,
+           const double2* __restrict__ twT, const double2* __restrict__ tw_mid, long long* prof) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int C = P::C, R1 = P::R1, NT = P::NT, RF = P::RF, BUF = P::BUF, Q = P::Q, S = P::S;
+    constexpr int N = P::N;
+    constexpr int NG = BUF / RF;
+    static_assert(P::ACC_TM && P::TMEM_TW && C >= 2 && Q == NT && NG == NT, "pipelined bootstrap: one item per thread");
+    static_assert(S * 8 == BUF * 16, "a rotated-accumulator half doubles as a staging buffer");
+    constexpr unsigned BUF_BYTES = (unsigned)(sizeof(double2) << P::LOGBUF);
+    const bool do_prof = (prof != nullptr) && blockIdx.x < 16 && threadIdx.x == 0;
+    long long t_last = do_prof ? clock64() : 0;
+#define PIPE_PROF(slot)                                  \
+    if (do_prof) {                                       \
+        const long long t_now = clock64();               \
+        prof[16 * blockIdx.x + slot] += t_now - t_last;  \
+        t_last = t_now;                                  \
+    }
+    u64* ra = reinterpret_cast<u64*>(smem_raw);                        // [2][S] rotated accumulator of the coming CMUX
+    double2* work = reinterpret_cast<double2*>(ra + 2 * (size_t)S);    // [4][BUF]
+    double2* xstg = work + 4 * (size_t)BUF;                            // [BUF] spare staging buffer
+    __shared__ __align__(8) u64 s_bar[8];     // 0..3: forward data of work buffer b; 4, 5: inverse data of output o; 6, 7: rotated polynomial c
+    const int tid = threadIdx.x;
+    const int rank = (int)cg::this_cluster().block_rank();
+    const long cluster_id = blockIdx.x / C, nclusters = gridDim.x / C;
+    const size_t ggsw_stride = (size_t)4 * 2 * C * BUF;               // double2 per CMUX iteration (J = 4, k + 1 = 2)
+    const int base_log = g.base_log;
+    const int nonrep = 64 - 2 * base_log;
+
+    const TwCtx tw = tw_setup<P>(nullptr, twT, tw_mid);
+    if (tid == 0) {
+        for (int b = 0; b < 8; b++) mbar_init(&s_bar[b], 1);
+        mbar_fence_init();
+        for (int b = 0; b < 6; b++) mbar_arm(&s_bar[b], BUF_BYTES);    // first CMUX: forward and inverse data
+    }
+    __syncthreads();
+    cg::this_cluster().sync();                // every CTA's barriers exist before the first remote access
+    unsigned ph = 0;
+    const int q = tid;
+    const int j2 = (rank << P::LOGQ) + q;
+    const int off = SW(j2) & (Q - 1);
+
+    for (long ct = cluster_id; ct < B; ct += nclusters) {
+        const u64* lwe = in + (size_t)ct * (g.n + 1);
+        const u64* lut = luts + (size_t)(lut_idx ? lut_idx[ct] : 0) * 2 * N;
+        int a_next = modswitch(lwe[0], g.logN);
+        {
+            // tensor memory: ACC = X^{-b~} * LUT; shared array: X^{a_0} * ACC, the operand of the first CMUX
+            const int a0 = (2 * N - modswitch(lwe[g.n], g.logN)) & (2 * N - 1);
+            const int a0s = (a0 + a_next) & (2 * N - 1);
+            for (int w = tid; w < 2 * S; w += NT) {
+                const int c = w >> P::LOGS, s = w & (S - 1);
+                const int v = (slot_to_coef<P>(s, rank) - a0s) & (2 * N - 1);
+                const u64 x = lut[(size_t)c * N + (v & (N - 1))];
+                ra[w] = (v >> (P::LOGM + 1)) ? (0ULL - x) : x;
+            }
+#pragma unroll 1
+            for (int c = 0; c < 2; c++) {
+                unsigned ow[4 * R1];
+#pragma unroll
+                for (int hj = 0; hj < 2 * R1; hj++) {
+                    const int v = ((hj << P::LOGL1) + j2 - a0) & (2 * N - 1);
+                    u64 x = lut[(size_t)c * N + (v & (N - 1))];
+                    if (v >> (P::LOGM + 1)) x = 0ULL - x;
+                    ow[2 * hj] = (unsigned)x;
+                    ow[2 * hj + 1] = (unsigned)(x >> 32);
+                }
+                TmemIo<4 * R1>::st(tw.tAcc + (unsigned)(c * 4 * R1), ow);
+            }
+            tmem_wait_st();
+        }
+        // the peers may still be in the last CMUX of their previous ciphertext: nothing of this one may reach them yet
+        cg::this_cluster().sync();
+        if (tid == 0) {                       // the first rotated accumulator was written locally: complete its phase
+            mbar_arrive(&s_bar[6]);
+            mbar_arrive(&s_bar[7]);
+        }
+
+        for (int i = 0; i < g.n; i++) {
+            const bool push = (i + 1 < g.n);
+            a_next = push ? modswitch(lwe[i + 1], g.logN) : 0;
+            // GGSW_{i+1} slices of this rank -> L2 one iteration ahead
+            if (push && tid < 8)
+                prefetch_l2_bulk(bskF + (size_t)(i + 1) * ggsw_stride + (((size_t)tid * C + rank) << P::LOGBUF), BUF_BYTES);
+            // ---------------- P1: decompose X^a * ACC - ACC, stage 1, bulk copies to the owners
+            {
+                double2 T[R1];
+                load_T<P>(T, tw, j2);
+                unsigned st[2 * R1];
+                double2 v[R1];
+                // polynomial 0
+                mbar_wait(&s_bar[6], ph);
+                PIPE_PROF(7)
+                if (tid == 0 && push) mbar_arm(&s_bar[6], BUF_BYTES);
+                pipe_read_state<P>(ra, tw.tAcc, q, nonrep, st);
+                __syncthreads();                                   // rotated polynomial 0 consumed: its half stages (0, lv 0)
+                PIPE_PROF(9)
+                pipe_emit_compute<P>(st, base_log, T, g, v);       // level index 1 (least significant digits)
+                pipe_stage<P>(xstg, off, v);
+                fence_proxy_async();
+                __syncthreads();
+                if (tid < C) pipe_send<P>(xstg, work + 2 * (size_t)BUF, &s_bar[2], rank, tid);
+                PIPE_PROF(10)
+                pipe_emit_compute<P>(st, base_log, T, g, v);       // level index 0
+                pipe_stage<P>(reinterpret_cast<double2*>(ra), off, v);
+                fence_proxy_async();
+                __syncthreads();
+                if (tid < C) pipe_send<P>(reinterpret_cast<double2*>(ra), work, &s_bar[0], rank, tid);
+                PIPE_PROF(11)
+                // polynomial 1
+                mbar_wait(&s_bar[7], ph);
+                PIPE_PROF(12)
+                if (tid == 0 && push) mbar_arm(&s_bar[7], BUF_BYTES);
+                pipe_read_state<P>(ra + S, tw.tAcc + (unsigned)(4 * R1), q, nonrep, st);
+                __syncthreads();
+                pipe_emit_compute<P>(st, base_log, T, g, v);
+                pipe_stage<P>(reinterpret_cast<double2*>(ra + S), off, v);
+                fence_proxy_async();
+                __syncthreads();
+                if (tid < C) pipe_send<P>(reinterpret_cast<double2*>(ra + S), work + 3 * (size_t)BUF, &s_bar[3], rank, tid);
+                PIPE_PROF(13)
+                // the spare staging buffer is used a second time: every CTA must have received the chunks staged in it
+                mbar_wait(&s_bar[2], ph);
+                cluster_arrive();
+                PIPE_PROF(14)
+                pipe_emit_compute<P>(st, base_log, T, g, v);
+                cluster_wait();
+                PIPE_PROF(15)
+                pipe_stage<P>(xstg, off, v);
+                fence_proxy_async();
+                __syncthreads();
+                if (tid < C) pipe_send<P>(xstg, work + (size_t)BUF, &s_bar[1], rank, tid);
+            }
+            PIPE_PROF(0)
+            // ---------------- P2: forward mid passes, polynomial 0 while polynomial 1 is still in flight
+            mbar_wait(&s_bar[0], ph);
+            mbar_wait(&s_bar[2], ph);
+            PIPE_PROF(1)
+            mid_pass<P::LRA, P::LOGL1, P::LOGBUF, NT, false, true>(work, 2, tw.tA, tw.sA, 2);
+            __syncthreads();
+            mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, NT, false, true>(work, 2, tw.tB, tw.sB, 2);
+            __syncthreads();
+            mbar_wait(&s_bar[1], ph);
+            mbar_wait(&s_bar[3], ph);
+            if (tid == 0)
+                for (int b = 0; b < 4; b++) mbar_arm(&s_bar[b], BUF_BYTES);      // next CMUX
+            mid_pass<P::LRA, P::LOGL1, P::LOGBUF, NT, false, true>(work + BUF, 2, tw.tA, tw.sA, 2);
+            __syncthreads();
+            mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, NT, false, true>(work + BUF, 2, tw.tB, tw.sB, 2);
+            __syncthreads();
+            PIPE_PROF(2)
+            // ---------------- P3: last forward pass + multiply-accumulate against GGSW_i + first inverse pass
+            {
+                const double2* gp = bskF + (size_t)i * ggsw_stride + ((size_t)rank << P::LOGBUF) + tid;
+                const size_t o_stride = (size_t)C << P::LOGBUF;
+                double2 r[2][RF], gv[2][RF];
+#pragma unroll
+                for (int o = 0; o < 2; o++)
+#pragma unroll
+                    for (int m = 0; m < RF; m++) {
+                        r[o][m] = make_double2(0.0, 0.0);
+                        gv[o][m] = __ldg(gp + o * o_stride + m * NG);
+                    }
+#pragma unroll 1
+                for (int j = 0; j < 4; j++) {
+                    double2 x[RF];
+                    const double2* base = work + ((size_t)(((j & 1) << 1) | (j >> 1)) << P::LOGBUF);
+#pragma unroll
+                    for (int m = 0; m < RF; m++) x[m] = base[SW(tid * RF + m)];
+                    Dft<RF, false>::run(x);
+                    const double2* gn = gp + (size_t)(j + 1) * 2 * o_stride;
+                    const bool more = (j + 1 < 4);
+#pragma unroll
+                    for (int o = 0; o < 2; o++)
+#pragma unroll
+                        for (int m = 0; m < RF; m++) {
+                            const double2 b = gv[o][m];
+                            r[o][m].x = fma(x[m].x, b.x, r[o][m].x);
+                            r[o][m].x = fma(-x[m].y, b.y, r[o][m].x);
+                            r[o][m].y = fma(x[m].x, b.y, r[o][m].y);
+                            r[o][m].y = fma(x[m].y, b.x, r[o][m].y);
+                            if (more) gv[o][m] = __ldg(gn + o * o_stride + m * NG);
+                        }
+                }
+#pragma unroll
+                for (int o = 0; o < 2; o++) {
+                    Dft<RF, true>::run(r[o]);
+                    double2* base = work + ((size_t)o << P::LOGBUF);
+#pragma unroll
+                    for (int m = 0; m < RF; m++) base[SW(tid * RF + m)] = r[o][m];
+                }
+            }
+            __syncthreads();
+            cluster_arrive();                 // "my buffers 2 and 3 are free": completes behind the inverse passes
+            PIPE_PROF(3)
+            // ---------------- P4: inverse mid passes of the two outputs, bulk copies to the owners' spare buffers
+            mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, NT, true, true>(work, 2, tw.tB, tw.sB);
+            __syncthreads();
+            mid_pass<P::LRA, P::LOGL1, P::LOGBUF, NT, true, true>(work, 2, tw.tA, tw.sA);
+            fence_proxy_async();
+            __syncthreads();
+            PIPE_PROF(4)
+            cluster_wait();
+            if (tid < 2 * C) {
+                const int o = tid / C, d = tid % C;
+                pipe_send<P>(work + ((size_t)o << P::LOGBUF), work + ((size_t)(2 + o) << P::LOGBUF), &s_bar[4 + o], rank, d);
+            }
+            PIPE_PROF(5)
+            // ---------------- P5: inverse radix-R1 stage, untwist, round, ACC += ; push X^{a'} * ACC to its readers
+            {
+                double2 T[R1];
+                load_T<P>(T, tw, j2);
+                const int u = j2 + (a_next & (P::L1 - 1));
+                const int j2d = u & (P::L1 - 1);
+                const int hbd = (a_next >> P::LOGL1) + (u >> P::LOGL1);
+                const int dcta = j2d >> P::LOGQ;
+#pragma unroll 1
+                for (int o = 0; o < 2; o++) {
+                    mbar_wait(&s_bar[4 + o], ph);
+                    if (tid == 0) mbar_arm(&s_bar[4 + o], BUF_BYTES);          // next CMUX
+                    double2 z[R1];
+                    stage1_gather_local<P>(work + ((size_t)(2 + o) << P::LOGBUF), j2, T, g, z);
+                    const unsigned dst = mapa_u32(smem_u32(ra + (size_t)o * S + (j2d & (Q - 1))), dcta);
+                    const unsigned dbar = mapa_u32(smem_u32(&s_bar[6 + o]), dcta);
+#pragma unroll
+                    for (int half = 0; half < 2; half++) {
+                        unsigned ow[2 * R1];
+                        const unsigned ta = tw.tAcc + (unsigned)(o * 4 * R1 + half * 2 * R1);
+                        TmemIo<2 * R1>::ld(ta, ow);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j1 = 0; j1 < R1; j1++) {
+                            const u64 v = (((u64)ow[2 * j1 + 1] << 32) | (u64)ow[2 * j1]) +
+                                          f2torus((half ? z[j1].y : z[j1].x) * g.inv_M);
+                            ow[2 * j1] = (unsigned)v;
+                            ow[2 * j1 + 1] = (unsigned)(v >> 32);
+                            if (push) {
+                                // coefficient p = hj*L1 + j2 lands on (p + a') mod N, negated when it wraps once
+                                const int bt = (half * R1 + j1 + hbd) & (4 * R1 - 1);
+                                st_async_u64(dst + ((unsigned)(bt & (2 * R1 - 1)) << (P::LOGQ + 3)),
+                                             (bt >> (P::LOGR1 + 1)) ? (0ULL - v) : v, dbar);
+                            }
+                        }
+                        TmemIo<2 * R1>::st(ta, ow);
+                    }
+                }
+                tmem_wait_st();
+            }
+            ph ^= 1u;
+            PIPE_PROF(6)
+        }
+        // ---- sample extract coefficient 0: the accumulator words are in the owners' tensor-memory lanes
+        {
+            u64* o = out + (size_t)ct * ((size_t)N + 1);
+#pragma unroll 1
+            for (int c = 0; c < 2; c++) {
+                unsigned ow[4 * R1];
+                TmemIo<4 * R1>::ld(tw.tAcc + (unsigned)(c * 4 * R1), ow);
+                tmem_wait_ld();
+#pragma unroll
+                for (int hj = 0; hj < 2 * R1; hj++) {
+                    const int j = (hj << P::LOGL1) + j2;
+                    const u64 v = ((u64)ow[2 * hj + 1] << 32) | (u64)ow[2 * hj];
+                    if (c == 0) {
+                        if (j == 0) o[0] = v;
+                        else o[N - j] = 0ULL - v;
+                    } else if (j == 0)
+                        o[N] = v;
+                }
+            }
+        }
+        PIPE_PROF(8)
+    }
+    cg::this_cluster().sync();                // nobody leaves while a peer could still address its shared memory
+    tw_teardown<P>(tw);
+#undef PIPE_PROF
+}

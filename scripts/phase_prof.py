@@ -44,7 +44,15 @@ for pbits, B in ((8, 36), (6, 148), (4, 888), ("w", 444)):
         print("   per-rank kcycles of cluster 0 (P1 | syncA | midF | fused | midI | syncB | P5 | syncC):")
         for r in range(min(C, 16)):
             print("     rank %2d: " % r + " ".join("%7.0f" % (allp[r, i] / 1e3) for i in range(8)))
-    extra = prof.cpu().numpy()[9:11].astype(np.float64)
-    print(f"   (thread 0 inside P1: loads+diff {extra[0] / 1e3:.0f} kcycles, level loop {extra[1] / 1e3:.0f} kcycles)")
+    extra = prof.cpu().numpy()[9:16].astype(np.float64)
+    if extra[2:].sum() > 0:
+        # pipelined kernel (pbs_pipe.cuh): slices of P1 in order; slot 0 above is the tail (stage + send of the last emit),
+        # "sync C" the wait for rotated polynomial 0, "sync A" the wait for the forward data of polynomial 0
+        names = ["read poly 0 + sync", "emit (0, lv1) + send", "emit (0, lv0) + send", "wait rotated poly 1",
+                 "read poly 1, emit (1, lv1) + send", "wait buffer 2 landed + arrive", "emit (1, lv0) compute + cluster wait"]
+        print("   P1 slices of the pipelined kernel (kcycles): " + "; ".join(f"{n} {v / 1e3:.0f}" for n, v in zip(names, extra)))
+        print(f"   P1 total {(extra.sum() + c[0]) / 1e3:.0f} kcycles; CMUX total {(c.sum() + extra.sum()) / 1e3:.0f} kcycles")
+    else:
+        print(f"   (thread 0 inside P1: loads+diff {extra[0] / 1e3:.0f} kcycles, level loop {extra[1] / 1e3:.0f} kcycles)")
     del ks, ev
     torch.cuda.empty_cache()

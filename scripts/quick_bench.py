@@ -24,7 +24,7 @@ SETS = {
     "p8": E.CryptoParams(p=8, n=996, k=1, N=32768, pbs_level=2, pbs_base_log=15, ks_level=7, ks_base_log=3,
                          lwe_std=6.7677e-8, glwe_std=2.168e-19),
 }
-BATCH = {"p4": 4096, "p5": 2048, "p6": 1024, "p8": 256}
+BATCH = {"p4": 4096, "p5": 2048, "p6": 1024, "p8": int(os.environ.get("QB_P8_BATCH", "240"))}   # p8: 15 clusters x 16 waves
 
 
 def flops_pbs(p):
