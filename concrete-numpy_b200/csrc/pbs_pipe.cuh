@@ -34,6 +34,19 @@ __device__ __forceinline__ void mbar_arrive(u64* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// x * scale (scale = 2^-64 / M) -> torus word: the fractional part of the scaled value, read straight out of the mantissa
+// of (frac + 1.5) in [1, 2].  5 FP64 + 3 integer operations instead of the 10 + 6 of f2torus; the result is rounded to a
+// multiple of 2^12 (2^-52 of the torus), 2^28 times below the fp64 FFT's own error at these sizes.
+__device__ __forceinline__ u64 f2torus_frac(double x, double scale) {
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
+    const double y = x * scale;
+    const double f = y - ((y + MAGIC) - MAGIC);              // y - rint(y) in [-0.5, 0.5], exact
+    const double t = f + 1.5;
+    const unsigned hi = (unsigned)__double2hiint(t), lo = (unsigned)__double2loint(t);
+    // mantissa << 12 (sign and exponent fall off the top), minus 2^63
+    return ((u64)(((hi << 12) | (lo >> 20)) ^ 0x80000000u) << 32) | (u64)(lo << 12);
+}
+
 // 32-bit decomposition states of the 2*R1 coefficients of this thread's item of one polynomial:
 // closest representable of (X^a * ACC - ACC); the rotated operand was pushed into `rac` by its producers,
 // the thread's own words wait in its tensor-memory lane
@@ -94,7 +107,12 @@ __device__ __forceinline__ void pipe_stage(double2* __restrict__ stg, int off, c
 
 // thread d < C: chunk d of `stg` -> chunk `rank` of work buffer `dst_buf` of CTA d, counted on its mbarrier `bar`
 template <class P>
-__device__ __forceinline__ void pipe_send(const double2* stg, double2* dst_buf, u64* bar, int rank, int d) {
+__device__ __forceinline__ void pipe_send(const double2* stg, double2* dst_buf, u64* bar, int rank, int d, bool self = false) {
+    if (self) {         // development ablation (FHE_PBS_DBG): same bytes, same barrier, no SM-to-SM traffic; results are wrong
+        bulk_copy_to_cluster(mapa_u32(smem_u32(dst_buf + (d << P::LOGQ)), rank), stg + (d << P::LOGQ),
+                             (unsigned)(sizeof(double2) << P::LOGQ), mapa_u32(smem_u32(bar), rank));
+        return;
+    }
     bulk_copy_to_cluster(mapa_u32(smem_u32(dst_buf + (rank << P::LOGQ)), d), stg + (d << P::LOGQ),
                          (unsigned)(sizeof(double2) << P::LOGQ), mapa_u32(smem_u32(bar), d));
 }
@@ -129,6 +147,7 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
     const size_t ggsw_stride = (size_t)4 * 2 * C * BUF;               // double2 per CMUX iteration (J = 4, k + 1 = 2)
     const int base_log = g.base_log;
     const int nonrep = 64 - 2 * base_log;
+    const double tscale = g.inv_M * 5.42101086242752217e-20;           // 2^-64 / M
 
     const TwCtx tw = tw_setup<P>(nullptr, twT, tw_mid);
     if (tid == 0) {
@@ -142,11 +161,21 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
     const int q = tid;
     const int j2 = (rank << P::LOGQ) + q;
     const int off = SW(j2) & (Q - 1);
+    // the R1 stage-1 twiddles of this thread's item never change: they live in the tensor-memory columns the plan leaves free
+    static_assert(2 * P::TM_THREAD + 2 * 4 * R1 <= 512 && P::TM_CTA == 512, "room for the stage-1 twiddles");
+    const unsigned tT = tw.base + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)(2 * P::TM_THREAD + (tid >> 7) * 4 * R1);
+    {
+        double2 T[R1];
+        load_T<P>(T, tw, j2);
+        tmem_store_c<R1>(tT, T);
+        tmem_wait_st();
+    }
 
     for (long ct = cluster_id; ct < B; ct += nclusters) {
         const u64* lwe = in + (size_t)ct * (g.n + 1);
         const u64* lut = luts + (size_t)(lut_idx ? lut_idx[ct] : 0) * 2 * N;
         int a_next = modswitch(lwe[0], g.logN);
+        u64 lwe_ahead = lwe[1];               // mask word i + 1, loaded one CMUX before its rotation amount is needed
         {
             // tensor memory: ACC = X^{-b~} * LUT; shared array: X^{a_0} * ACC, the operand of the first CMUX
             const int a0 = (2 * N - modswitch(lwe[g.n], g.logN)) & (2 * N - 1);
@@ -181,14 +210,15 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
 
         for (int i = 0; i < g.n; i++) {
             const bool push = (i + 1 < g.n);
-            a_next = push ? modswitch(lwe[i + 1], g.logN) : 0;
+            a_next = push ? modswitch(lwe_ahead, g.logN) : 0;
+            if (i + 2 < g.n) lwe_ahead = lwe[i + 2];
             // GGSW_{i+1} slices of this rank -> L2 one iteration ahead
             if (push && tid < 8)
                 prefetch_l2_bulk(bskF + (size_t)(i + 1) * ggsw_stride + (((size_t)tid * C + rank) << P::LOGBUF), BUF_BYTES);
             // ---------------- P1: decompose X^a * ACC - ACC, stage 1, bulk copies to the owners
             {
                 double2 T[R1];
-                load_T<P>(T, tw, j2);
+                tmem_load_c<R1>(tT, T);
                 unsigned st[2 * R1];
                 double2 v[R1];
                 // polynomial 0
@@ -200,15 +230,15 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 PIPE_PROF(9)
                 pipe_emit_compute<P>(st, base_log, T, g, v);       // level index 1 (least significant digits)
                 pipe_stage<P>(xstg, off, v);
-                fence_proxy_async();
                 __syncthreads();
-                if (tid < C) pipe_send<P>(xstg, work + 2 * (size_t)BUF, &s_bar[2], rank, tid);
+                if (tid < C) fence_proxy_async();     // staged before the barrier: one fence in the issuing thread
+                if (tid < C) pipe_send<P>(xstg, work + 2 * (size_t)BUF, &s_bar[2], rank, tid, g.dbg & 2);
                 PIPE_PROF(10)
                 pipe_emit_compute<P>(st, base_log, T, g, v);       // level index 0
                 pipe_stage<P>(reinterpret_cast<double2*>(ra), off, v);
-                fence_proxy_async();
                 __syncthreads();
-                if (tid < C) pipe_send<P>(reinterpret_cast<double2*>(ra), work, &s_bar[0], rank, tid);
+                if (tid < C) fence_proxy_async();     // staged before the barrier: one fence in the issuing thread
+                if (tid < C) pipe_send<P>(reinterpret_cast<double2*>(ra), work, &s_bar[0], rank, tid, g.dbg & 2);
                 PIPE_PROF(11)
                 // polynomial 1
                 mbar_wait(&s_bar[7], ph);
@@ -218,9 +248,9 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 __syncthreads();
                 pipe_emit_compute<P>(st, base_log, T, g, v);
                 pipe_stage<P>(reinterpret_cast<double2*>(ra + S), off, v);
-                fence_proxy_async();
                 __syncthreads();
-                if (tid < C) pipe_send<P>(reinterpret_cast<double2*>(ra + S), work + 3 * (size_t)BUF, &s_bar[3], rank, tid);
+                if (tid < C) fence_proxy_async();     // staged before the barrier: one fence in the issuing thread
+                if (tid < C) pipe_send<P>(reinterpret_cast<double2*>(ra + S), work + 3 * (size_t)BUF, &s_bar[3], rank, tid, g.dbg & 2);
                 PIPE_PROF(13)
                 // the spare staging buffer is used a second time: every CTA must have received the chunks staged in it
                 mbar_wait(&s_bar[2], ph);
@@ -230,9 +260,9 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 cluster_wait();
                 PIPE_PROF(15)
                 pipe_stage<P>(xstg, off, v);
-                fence_proxy_async();
                 __syncthreads();
-                if (tid < C) pipe_send<P>(xstg, work + (size_t)BUF, &s_bar[1], rank, tid);
+                if (tid < C) fence_proxy_async();     // staged before the barrier: one fence in the issuing thread
+                if (tid < C) pipe_send<P>(xstg, work + (size_t)BUF, &s_bar[1], rank, tid, g.dbg & 2);
             }
             PIPE_PROF(0)
             // ---------------- P2: forward mid passes, polynomial 0 while polynomial 1 is still in flight
@@ -249,21 +279,25 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 for (int b = 0; b < 4; b++) mbar_arm(&s_bar[b], BUF_BYTES);      // next CMUX
             mid_pass<P::LRA, P::LOGL1, P::LOGBUF, NT, false, true>(work + BUF, 2, tw.tA, tw.sA, 2);
             __syncthreads();
+            // the GGSW values of the first digit polynomial are requested before the last mid pass: their L2 latency
+            // hides behind it instead of opening the multiply-accumulate
+            const double2* gp = bskF + (size_t)i * ggsw_stride + ((size_t)rank << P::LOGBUF) + tid;
+            const size_t o_stride = (size_t)C << P::LOGBUF;
+            double2 gv[2][RF];
+#pragma unroll
+            for (int o = 0; o < 2; o++)
+#pragma unroll
+                for (int m = 0; m < RF; m++) gv[o][m] = __ldg(gp + o * o_stride + m * NG);
             mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, NT, false, true>(work + BUF, 2, tw.tB, tw.sB, 2);
             __syncthreads();
             PIPE_PROF(2)
             // ---------------- P3: last forward pass + multiply-accumulate against GGSW_i + first inverse pass
             {
-                const double2* gp = bskF + (size_t)i * ggsw_stride + ((size_t)rank << P::LOGBUF) + tid;
-                const size_t o_stride = (size_t)C << P::LOGBUF;
-                double2 r[2][RF], gv[2][RF];
+                double2 r[2][RF];
 #pragma unroll
                 for (int o = 0; o < 2; o++)
 #pragma unroll
-                    for (int m = 0; m < RF; m++) {
-                        r[o][m] = make_double2(0.0, 0.0);
-                        gv[o][m] = __ldg(gp + o * o_stride + m * NG);
-                    }
+                    for (int m = 0; m < RF; m++) r[o][m] = make_double2(0.0, 0.0);
 #pragma unroll 1
                 for (int j = 0; j < 4; j++) {
                     double2 x[RF];
@@ -300,23 +334,23 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
             mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, NT, true, true>(work, 2, tw.tB, tw.sB);
             __syncthreads();
             mid_pass<P::LRA, P::LOGL1, P::LOGBUF, NT, true, true>(work, 2, tw.tA, tw.sA);
-            fence_proxy_async();
             __syncthreads();
             PIPE_PROF(4)
             cluster_wait();
             if (tid < 2 * C) {
+                fence_proxy_async();
                 const int o = tid / C, d = tid % C;
-                pipe_send<P>(work + ((size_t)o << P::LOGBUF), work + ((size_t)(2 + o) << P::LOGBUF), &s_bar[4 + o], rank, d);
+                pipe_send<P>(work + ((size_t)o << P::LOGBUF), work + ((size_t)(2 + o) << P::LOGBUF), &s_bar[4 + o], rank, d, g.dbg & 4);
             }
             PIPE_PROF(5)
             // ---------------- P5: inverse radix-R1 stage, untwist, round, ACC += ; push X^{a'} * ACC to its readers
             {
                 double2 T[R1];
-                load_T<P>(T, tw, j2);
+                tmem_load_c<R1>(tT, T);
                 const int u = j2 + (a_next & (P::L1 - 1));
                 const int j2d = u & (P::L1 - 1);
                 const int hbd = (a_next >> P::LOGL1) + (u >> P::LOGL1);
-                const int dcta = j2d >> P::LOGQ;
+                const int dcta = (g.dbg & 1) ? rank : (j2d >> P::LOGQ);
 #pragma unroll 1
                 for (int o = 0; o < 2; o++) {
                     mbar_wait(&s_bar[4 + o], ph);
@@ -334,7 +368,7 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
 #pragma unroll
                         for (int j1 = 0; j1 < R1; j1++) {
                             const u64 v = (((u64)ow[2 * j1 + 1] << 32) | (u64)ow[2 * j1]) +
-                                          f2torus((half ? z[j1].y : z[j1].x) * g.inv_M);
+                                          f2torus_frac(half ? z[j1].y : z[j1].x, tscale);
                             ow[2 * j1] = (unsigned)v;
                             ow[2 * j1 + 1] = (unsigned)(v >> 32);
                             if (push) {
