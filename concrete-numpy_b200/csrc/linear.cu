@@ -99,11 +99,13 @@ k_rows(u64* __restrict__ out, const u64* __restrict__ a, const u64* __restrict__
 }
 
 // ---- general clear-weighted gather: out[e] = sum_j w[e][j] * x[idx[e][j]] (+ bias on body)
-// idx < 0 or w == 0 => no term: the taps of an output row are compacted into shared memory once per CTA (zero weights
-// of ternary matrices and padding cost nothing in the inner loop).  Covers dot / conv2d / sum and the matmuls the
-// tiled kernel does not take; grid = (E, column chunks), GM_TPT columns per thread, coalesced 8-byte accesses
-// (operand rows start on either 16-byte phase).  More than a few taps per output make this kernel INT-ALU bound
-// (3 IMAD per u64 multiply-add), not HBM bound: see DESIGN.md 4.3.
+// idx < 0 or w == 0 => no term.  The taps of an output row are compacted into shared memory once per CTA by its first
+// warp (ballot + prefix count), grouped as [+1 taps | -1 taps | general taps]: zero weights of ternary matrices and
+// padding cost nothing, and +-1 weights (convolution stencils, sums, concatenations) are plain 64-bit adds instead of
+// three 32-bit multiply-adds.  Covers dot / conv2d / sum and the matmuls the tiled kernels do not take;
+// grid = (E, column chunks), GM_TPT columns per thread, coalesced 8-byte accesses (operand rows start on either
+// 16-byte phase).  Operand rows shared by neighbouring outputs (convolutions) are re-read from L2, so with many taps
+// per output this kernel is bound by L2 -> SM traffic and 64-bit integer adds, not by HBM: see DESIGN.md 4.3.
 #define GM_TPT 8
 #define GM_MAXTAPS 1024
 __global__ void __launch_bounds__(256)
@@ -111,31 +113,61 @@ k_gather_mac(u64* __restrict__ out, const u64* __restrict__ x, const int* __rest
              const i64* __restrict__ w, const u64* __restrict__ bias, int K, int L) {
     __shared__ int s_src[GM_MAXTAPS];
     __shared__ i64 s_w[GM_MAXTAPS];
-    __shared__ int s_cnt;
+    __shared__ int s_cnt[3];
     const long e = blockIdx.x;
     const int* ie = idx + (size_t)e * K;
     const i64* we = w + (size_t)e * K;
     const u64 be = bias ? bias[e] : 0ULL;
     for (int k0 = 0; k0 < K; k0 += GM_MAXTAPS) {        // (K > GM_MAXTAPS: several rounds, accumulating into out)
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int c = 0;
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
             const int k1 = (K - k0 < GM_MAXTAPS) ? K - k0 : GM_MAXTAPS;
-            for (int j = 0; j < k1; j++) {
-                const int sidx = ie[k0 + j];
-                const i64 wj = we[k0 + j];
-                if (sidx >= 0 && wj != 0) { s_src[c] = sidx; s_w[c] = wj; c++; }
+            int c = 0;
+            for (int cls = 0; cls < 3; cls++) {             // +1, -1, everything else
+                const int c_start = c;
+                for (int j0 = 0; j0 < k1; j0 += 32) {
+                    const int j = j0 + lane;
+                    const int sidx = (j < k1) ? ie[k0 + j] : -1;
+                    const i64 wj = (j < k1) ? we[k0 + j] : 0;
+                    const int kind = (wj == 1) ? 0 : (wj == -1) ? 1 : 2;
+                    const bool keep = sidx >= 0 && wj != 0 && kind == cls;
+                    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+                    if (keep) {
+                        const int pos = c + __popc(mask & ((1u << lane) - 1u));
+                        s_src[pos] = sidx;
+                        s_w[pos] = wj;
+                    }
+                    c += __popc(mask);
+                }
+                if (lane == 0) s_cnt[cls] = c - c_start;
             }
-            s_cnt = c;
         }
         __syncthreads();
-        const int cnt = s_cnt;
+        const int cp = s_cnt[0], cn = s_cnt[1], cg = s_cnt[2];
         for (int t0 = blockIdx.y * blockDim.x * GM_TPT + threadIdx.x; t0 < L;
              t0 += gridDim.y * blockDim.x * GM_TPT) {
             u64 acc[GM_TPT];
 #pragma unroll
             for (int u = 0; u < GM_TPT; u++) acc[u] = 0;
-            for (int j = 0; j < cnt; j++) {
+            int j = 0;
+            for (; j < cp; j++) {
+                const u64* src = x + (size_t)s_src[j] * L;
+#pragma unroll
+                for (int u = 0; u < GM_TPT; u++) {
+                    const int t = t0 + u * blockDim.x;
+                    if (t < L) acc[u] += src[t];
+                }
+            }
+            for (; j < cp + cn; j++) {
+                const u64* src = x + (size_t)s_src[j] * L;
+#pragma unroll
+                for (int u = 0; u < GM_TPT; u++) {
+                    const int t = t0 + u * blockDim.x;
+                    if (t < L) acc[u] -= src[t];
+                }
+            }
+            for (; j < cp + cn + cg; j++) {
                 const u64 wj = (u64)s_w[j];
                 const u64* src = x + (size_t)s_src[j] * L;
 #pragma unroll
@@ -192,45 +224,94 @@ k_matmul(u64* __restrict__ out, const u64* __restrict__ x, const i64* __restrict
 }
 
 // ---- matmul with the operand tile staged in shared memory: x is read from HBM exactly ONCE.
-// CTA (m, chunk of MS_TC words): x[m][0..K)[chunk] -> shared memory (K x 512 B), the non-zero weights of every output
-// column n compacted to (k, w) lists (ternary / sparse weight matrices cost only their non-zeros), then every
-// (n, word) output is a short sum over its list read from shared memory.  Algorithmic bytes = traffic:
-// (Mr*K + Mr*Nc)*L*8.  Requires int32 weights and K*MS_TC*8 + Nc*K*6 + Nc*4 bytes of shared memory.
+// The weight matrices of FHE circuits are small clear integers and mostly sparse (ternary layers, convolution
+// stencils), so the columns of W are first compacted -- once per launch, by k_mm_taps -- into tap lists
+//   [+1 taps | -1 taps | general taps]   (k indices, i64 weights for the general ones: any 64-bit weight is exact)
+// and the main kernel does one add / subtract / multiply-add per NON-ZERO weight.
+// CTA (m, chunk of MS_TC words): x[m][0..K)[chunk] -> shared memory with 8-byte cp.async (rows start on either 16-byte
+// phase), then warp w owns output columns n = w, w + 8, ...: its lanes hold two word columns each (lane, lane + 32),
+// tap lists are read warp-uniformly through the read-only cache, operand words come from shared memory.
+// Algorithmic bytes = HBM traffic: (Mr*K + Mr*Nc)*L*8.  Dense matrices (more than half the weights non-zero) go to the
+// register-blocked k_matmul above, which is bound by the 64-bit integer multiply-adds, not by HBM.
 #define MS_TC 64
+struct MmTaps {            // scratch layout, one launch
+    int* cnt;              // [Nc][3]  number of +1, -1, general taps
+    unsigned short* kk;    // [Nc][K]  their k, grouped in that order
+    i64* ww;               // [Nc][K]  weights (aligned with kk; only the general ones are read)
+    int* sparse;           // 1: k_matmul_taps runs, 0: k_matmul runs
+};
+__global__ void k_mm_taps(const i64* __restrict__ W, int K, int Nc, MmTaps t) {
+    __shared__ int s_nnz;
+    if (threadIdx.x == 0) s_nnz = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int n = threadIdx.x; n < Nc; n += blockDim.x) {
+        unsigned short* kn = t.kk + (size_t)n * K;
+        i64* wn = t.ww + (size_t)n * K;
+        int c = 0, c0, c1;
+        for (int k = 0; k < K; k++) if (W[(size_t)k * Nc + n] == 1) kn[c++] = (unsigned short)k;
+        c0 = c;
+        for (int k = 0; k < K; k++) if (W[(size_t)k * Nc + n] == -1) kn[c++] = (unsigned short)k;
+        c1 = c;
+        for (int k = 0; k < K; k++) {
+            const i64 w = W[(size_t)k * Nc + n];
+            if (w != 0 && w != 1 && w != -1) { kn[c] = (unsigned short)k; wn[c] = w; c++; }
+        }
+        t.cnt[3 * n] = c0; t.cnt[3 * n + 1] = c1 - c0; t.cnt[3 * n + 2] = c - c1;
+        mine += c;
+    }
+    atomicAdd(&s_nnz, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) *t.sparse = (2L * s_nnz <= (long)K * Nc) ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(256)
-k_matmul_staged(u64* __restrict__ out, const u64* __restrict__ x, const i64* __restrict__ W, int K, int Nc, int L,
-                const int* __restrict__ run_if_set) {
+k_matmul_taps(u64* __restrict__ out, const u64* __restrict__ x, int K, int Nc, int L, MmTaps t) {
     extern __shared__ __align__(16) unsigned char ms_raw[];
-    if (!*run_if_set) return;                          // some weight needs more than 32 bits: the dense kernel runs
-    u64* xt = reinterpret_cast<u64*>(ms_raw);                              // [K][MS_TC]
-    int* ww = reinterpret_cast<int*>(xt + (size_t)K * MS_TC);              // [Nc][K] weights of the kept taps
-    int* cnt = ww + (size_t)Nc * K;                                         // [Nc]
-    unsigned short* kk = reinterpret_cast<unsigned short*>(cnt + Nc);       // [Nc][K] their k
+    if (!*t.sparse) return;                               // dense weights: k_matmul takes this product
+    u64* xt = reinterpret_cast<u64*>(ms_raw);             // [K][MS_TC]
     const long m = blockIdx.x;
     const int t0 = blockIdx.y * MS_TC;
-    const u64* xm = x + (size_t)m * K * L;
+    const u64* xm = x + (size_t)m * K * L + t0;
+    const int ncol = (L - t0 < MS_TC) ? L - t0 : MS_TC;
+    // stage the tile: consecutive threads copy consecutive words of a row (8-byte asynchronous copies, no registers)
     for (int i = threadIdx.x; i < K * MS_TC; i += blockDim.x) {
         const int k = i / MS_TC, c = i - k * MS_TC;
-        xt[i] = (t0 + c < L) ? xm[(size_t)k * L + t0 + c] : 0ULL;
+        if (c < ncol) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(xt + i);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(xm + (size_t)k * L + c) : "memory");
+        } else
+            xt[i] = 0ULL;
     }
-    for (int n = threadIdx.x; n < Nc; n += blockDim.x) {
-        int c = 0;
-        for (int k = 0; k < K; k++) {
-            const i64 wv = W[(size_t)k * Nc + n];
-            if (wv != 0) { kk[(size_t)n * K + c] = (unsigned short)k; ww[(size_t)n * K + c] = (int)wv; c++; }
-        }
-        cnt[n] = c;
-    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    const int c = threadIdx.x & (MS_TC - 1);
-    if (t0 + c >= L) return;
-    for (int n = threadIdx.x / MS_TC; n < Nc; n += blockDim.x / MS_TC) {
-        const int cn = cnt[n];
-        const unsigned short* kn = kk + (size_t)n * K;
-        const int* wn = ww + (size_t)n * K;
-        u64 acc = 0;
-        for (int j = 0; j < cn; j++) acc += (u64)(i64)wn[j] * xt[(int)kn[j] * MS_TC + c];
-        out[((size_t)m * Nc + n) * L + t0 + c] = acc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int n = warp; n < Nc; n += nwarps) {
+        const int cp = __ldg(t.cnt + 3 * n), cn = __ldg(t.cnt + 3 * n + 1), cg = __ldg(t.cnt + 3 * n + 2);
+        const unsigned short* kn = t.kk + (size_t)n * K;
+        const i64* wn = t.ww + (size_t)n * K;
+        u64 a0 = 0, a1 = 0, b0 = 0, b1 = 0;                // two word columns, two independent chains each
+        int j = 0;
+        for (; j + 1 < cp; j += 2) {
+            const u64* r0 = xt + (int)__ldg(kn + j) * MS_TC + lane;
+            const u64* r1 = xt + (int)__ldg(kn + j + 1) * MS_TC + lane;
+            a0 += r0[0]; a1 += r0[32]; b0 += r1[0]; b1 += r1[32];
+        }
+        if (j < cp) { const u64* r0 = xt + (int)__ldg(kn + j) * MS_TC + lane; a0 += r0[0]; a1 += r0[32]; j++; }
+        for (; j + 1 < cp + cn; j += 2) {
+            const u64* r0 = xt + (int)__ldg(kn + j) * MS_TC + lane;
+            const u64* r1 = xt + (int)__ldg(kn + j + 1) * MS_TC + lane;
+            a0 -= r0[0]; a1 -= r0[32]; b0 -= r1[0]; b1 -= r1[32];
+        }
+        if (j < cp + cn) { const u64* r0 = xt + (int)__ldg(kn + j) * MS_TC + lane; a0 -= r0[0]; a1 -= r0[32]; j++; }
+        for (; j < cp + cn + cg; j++) {
+            const u64 w = (u64)__ldg(wn + j);
+            const u64* r0 = xt + (int)__ldg(kn + j) * MS_TC + lane;
+            a0 += w * r0[0]; a1 += w * r0[32];
+        }
+        u64* o = out + ((size_t)m * Nc + n) * L + t0;
+        if (lane < ncol) o[lane] = a0 + b0;
+        if (lane + 32 < ncol) o[lane + 32] = a1 + b1;
     }
 }
 
@@ -246,16 +327,12 @@ static inline int sm_count() {
     return g_sm_count;
 }
 
+// column chunks of a row of L words: a remainder under a quarter of a block (L = k*N + 1: the body word) does not get a
+// block of its own, the kernels' grid-stride loops give it to the first block as a second trip
 static inline int col_chunks(int L, int per_block) {
-    int c = (L + per_block - 1) / per_block;
+    int c = L / per_block;
+    if (L - c * per_block >= per_block / 4) c++;
     return c < 1 ? 1 : (c > 64 ? 64 : c);
-}
-
-// do all weights fit a signed 32-bit integer?  Decided ON DEVICE (no host synchronisation inside Server.run): flag
-// stays 1 unless some weight does not fit; both matmul kernels are enqueued and the one the flag rules out exits at once.
-__global__ void k_weights_fit(const i64* __restrict__ W, long n, int* flag) {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-        if (W[i] != (i64)(int)W[i]) *flag = 0;
 }
 
 extern "C" {
@@ -354,32 +431,29 @@ int fhe_matmul_ct_clear(u64* out, const u64* x, const i64* W, long Mr, int K, in
     if (Mr == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem_dense = (size_t)K * MM_TN * sizeof(i64);
-    const size_t smem_staged = (size_t)K * MS_TC * 8 + (size_t)Nc * K * 6 + (size_t)Nc * 4 + 16;
-    const bool staged_ok = K <= 65535 && smem_staged <= 200 * 1024;
-    const bool dense_ok = smem_dense <= 48 * 1024;
-    if (!staged_ok && !dense_ok) FHE_FAIL(3, "matmul_ct_clear: K=%d too large for the tiled kernels (use gather_mac)", K);
-    int* d_flag = nullptr;
-    if (staged_ok) {
-        // staged kernel (x read once, sparse weights cost their non-zeros) when every weight fits 32 bits
-        FHE_CUDA(cudaMallocAsync(&d_flag, sizeof(int), st));
-        FHE_CUDA(cudaMemsetAsync(d_flag, 1, sizeof(int), st));          // non-zero = "staged kernel runs"
-        if (dense_ok) {
-            const long n = (long)K * Nc;
-            k_weights_fit<<<(unsigned)((n + 255) / 256 < 64 ? (n + 255) / 256 : 64), 256, 0, st>>>(W, n, d_flag);
-        }
-        // (no dense fallback for this K: the staged kernel must run; weights would be truncated to 32 bits only if the
-        // caller handed over wider ones, which FHE circuits -- clear ints of at most 17 bits -- never do)
-        FHE_CUDA(cudaFuncSetAttribute(k_matmul_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
-        dim3 grid((unsigned)Mr, (unsigned)((L + MS_TC - 1) / MS_TC));
-        k_matmul_staged<<<grid, 256, smem_staged, st>>>(out, x, W, K, Nc, L, d_flag);
-        FHE_CHECK_LAUNCH();
-    }
-    if (dense_ok) {
-        dim3 grid((unsigned)Mr, (Nc + MM_TN - 1) / MM_TN, col_chunks(L, 256));
-        k_matmul<<<grid, 256, smem_dense, st>>>(out, x, W, K, Nc, L, d_flag);
-        FHE_CHECK_LAUNCH();
-    }
-    if (d_flag) FHE_CUDA(cudaFreeAsync(d_flag, st));
+    const size_t smem_taps = (size_t)K * MS_TC * 8;
+    if (smem_dense > 48 * 1024 || smem_taps > 200 * 1024)
+        FHE_FAIL(3, "matmul_ct_clear: K=%d too large for the tiled kernels (use gather_mac)", K);
+    // which kernel runs is decided ON DEVICE by the density of W (no host synchronisation inside Server.run): both are
+    // enqueued and the one the flag rules out exits at once
+    unsigned char* scratch = nullptr;
+    MmTaps t = {};
+    const size_t b_cnt = ((size_t)Nc * 3 * sizeof(int) + 15) & ~(size_t)15;
+    const size_t b_kk = ((size_t)Nc * K * sizeof(unsigned short) + 15) & ~(size_t)15;
+    const size_t b_ww = (size_t)Nc * K * sizeof(i64);
+    FHE_CUDA(cudaMallocAsync(&scratch, b_cnt + b_kk + b_ww + 16, st));
+    t.cnt = reinterpret_cast<int*>(scratch);
+    t.kk = reinterpret_cast<unsigned short*>(scratch + b_cnt);
+    t.ww = reinterpret_cast<i64*>(scratch + b_cnt + b_kk);
+    t.sparse = reinterpret_cast<int*>(scratch + b_cnt + b_kk + b_ww);
+    k_mm_taps<<<1, 256, 0, st>>>(W, K, Nc, t);
+    FHE_CHECK_LAUNCH();
+    FHE_CUDA(cudaFuncSetAttribute(k_matmul_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_taps));
+    k_matmul_taps<<<dim3((unsigned)Mr, (unsigned)((L + MS_TC - 1) / MS_TC)), 256, smem_taps, st>>>(out, x, K, Nc, L, t);
+    FHE_CHECK_LAUNCH();
+    k_matmul<<<dim3((unsigned)Mr, (Nc + MM_TN - 1) / MM_TN, col_chunks(L, 256)), 256, smem_dense, st>>>(out, x, W, K, Nc, L, t.sparse);
+    FHE_CHECK_LAUNCH();
+    if (scratch) FHE_CUDA(cudaFreeAsync(scratch, st));
     return 0;
 }
 

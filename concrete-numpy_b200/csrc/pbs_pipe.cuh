@@ -15,8 +15,10 @@
 //     polynomial in the destination, so the next CMUX starts on polynomial 0 while polynomial 1 still drains.
 //
 // No cluster-wide release/acquire barrier (MEMBAR.ALL.GPU + drain) is left inside a CMUX: a CTA waits only for the
-// bytes it is about to read.  The hardware cluster barrier is used twice per CMUX in its relaxed split form
-// (arrive early, wait late): "staging buffer X has been read by every destination" and "my spare buffers are free".
+// bytes it is about to read.  The hardware cluster barrier is used three times per CMUX in its relaxed split form
+// (arrive early, wait late): "every CTA has finished the previous CMUX" (its work buffers may be overwritten: a CTA's
+// rotated accumulator comes from two peers only, so its arrival says nothing about the other five), "staging buffer X
+// has been read by every destination" and "my spare buffers are free".
 //
 // Buffer map (level = 2): digit polynomial (c, lv) lives in work buffer 2*lv + c.  The buffers polynomial 0 is sent to
 // (0 and 2) are exactly the ones whose previous contents -- output 0 and the inverse exchange of output 0 -- are known
@@ -157,6 +159,7 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
     }
     __syncthreads();
     cg::this_cluster().sync();                // every CTA's barriers exist before the first remote access
+    cluster_arrive();                         // pairs with the wait of the first CMUX ("previous CMUX finished everywhere")
     unsigned ph = 0;
     const int q = tid;
     const int j2 = (rank << P::LOGQ) + q;
@@ -201,8 +204,7 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
             }
             tmem_wait_st();
         }
-        // the peers may still be in the last CMUX of their previous ciphertext: nothing of this one may reach them yet
-        cg::this_cluster().sync();
+        __syncthreads();
         if (tid == 0) {                       // the first rotated accumulator was written locally: complete its phase
             mbar_arrive(&s_bar[6]);
             mbar_arrive(&s_bar[7]);
@@ -230,14 +232,17 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 PIPE_PROF(9)
                 pipe_emit_compute<P>(st, base_log, T, g, v);       // level index 1 (least significant digits)
                 pipe_stage<P>(xstg, off, v);
+                fence_proxy_async();                 // every writer: its staged values must be visible to the copy engine
                 __syncthreads();
-                if (tid < C) fence_proxy_async();     // staged before the barrier: one fence in the issuing thread
+                // nothing of this CMUX may reach a peer that has not finished the previous one (it still reads its spare
+                // buffers and its inverse copies still read its output buffers); also covers the ciphertext boundary
+                cluster_wait();
                 if (tid < C) pipe_send<P>(xstg, work + 2 * (size_t)BUF, &s_bar[2], rank, tid, g.dbg & 2);
                 PIPE_PROF(10)
                 pipe_emit_compute<P>(st, base_log, T, g, v);       // level index 0
                 pipe_stage<P>(reinterpret_cast<double2*>(ra), off, v);
+                fence_proxy_async();                 // every writer: its staged values must be visible to the copy engine
                 __syncthreads();
-                if (tid < C) fence_proxy_async();     // staged before the barrier: one fence in the issuing thread
                 if (tid < C) pipe_send<P>(reinterpret_cast<double2*>(ra), work, &s_bar[0], rank, tid, g.dbg & 2);
                 PIPE_PROF(11)
                 // polynomial 1
@@ -248,8 +253,8 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 __syncthreads();
                 pipe_emit_compute<P>(st, base_log, T, g, v);
                 pipe_stage<P>(reinterpret_cast<double2*>(ra + S), off, v);
+                fence_proxy_async();                 // every writer: its staged values must be visible to the copy engine
                 __syncthreads();
-                if (tid < C) fence_proxy_async();     // staged before the barrier: one fence in the issuing thread
                 if (tid < C) pipe_send<P>(reinterpret_cast<double2*>(ra + S), work + 3 * (size_t)BUF, &s_bar[3], rank, tid, g.dbg & 2);
                 PIPE_PROF(13)
                 // the spare staging buffer is used a second time: every CTA must have received the chunks staged in it
@@ -260,8 +265,8 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 cluster_wait();
                 PIPE_PROF(15)
                 pipe_stage<P>(xstg, off, v);
+                fence_proxy_async();                 // every writer: its staged values must be visible to the copy engine
                 __syncthreads();
-                if (tid < C) fence_proxy_async();     // staged before the barrier: one fence in the issuing thread
                 if (tid < C) pipe_send<P>(xstg, work + (size_t)BUF, &s_bar[1], rank, tid, g.dbg & 2);
             }
             PIPE_PROF(0)
@@ -334,11 +339,11 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
             mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, NT, true, true>(work, 2, tw.tB, tw.sB);
             __syncthreads();
             mid_pass<P::LRA, P::LOGL1, P::LOGBUF, NT, true, true>(work, 2, tw.tA, tw.sA);
+            fence_proxy_async();
             __syncthreads();
             PIPE_PROF(4)
             cluster_wait();
             if (tid < 2 * C) {
-                fence_proxy_async();
                 const int o = tid / C, d = tid % C;
                 pipe_send<P>(work + ((size_t)o << P::LOGBUF), work + ((size_t)(2 + o) << P::LOGBUF), &s_bar[4 + o], rank, d, g.dbg & 4);
             }
@@ -383,6 +388,7 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 }
                 tmem_wait_st();
             }
+            cluster_arrive();                 // "I have finished this CMUX": awaited before the first send of the next one
             ph ^= 1u;
             PIPE_PROF(6)
         }
@@ -408,6 +414,7 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
         }
         PIPE_PROF(8)
     }
+    cluster_wait();                           // pairs with the arrive of the last CMUX
     cg::this_cluster().sync();                // nobody leaves while a peer could still address its shared memory
     tw_teardown<P>(tw);
 #undef PIPE_PROF

@@ -334,8 +334,10 @@ def test_linear_kernels_all_paths_bit_exact(oracle, cuda_device, L):
         c = rng.integers(-(1 << 40), 1 << 40, Erows).astype(np.int64)
         assert np.array_equal(E.to_np_u64(E.lin_mul_clear(da, torch.from_numpy(c).to(cuda_device), L, ia)),
                               a[ia_np] * c.view(np.uint64)[:, None])
-    # matmul: sparse ternary weights (staged kernel), dense small weights, and 40-bit weights (dense fallback)
+    # matmul: sparse ternary weights (tap-list kernel), sparse weights mixing +-1 with small and 40-bit values (odd tap
+    # counts, a ragged last column chunk), dense small weights and dense 40-bit weights (register-blocked kernel)
     for Mr, K, Nc, wgen in [(3, 128, 64, lambda: rng.choice([-1, 0, 0, 0, 0, 0, 0, 1], (128, 64))),
+                            (2, 37, 9, lambda: rng.choice([-1, 0, 0, 0, 0, 0, 0, 1, 5, -(1 << 40)], (37, 9))),
                             (4, 5, 3, lambda: rng.integers(-9, 10, (5, 3))),
                             (2, 6, 17, lambda: rng.integers(-(1 << 40), 1 << 40, (6, 17)))]:
         x = rng.integers(0, 1 << 64, (Mr * K, L), dtype=np.uint64)
