@@ -196,9 +196,9 @@ k_gather_mac(u64* __restrict__ out, const u64* __restrict__ x, const int* __rest
 #define MM_TN 16
 __global__ void __launch_bounds__(256)
 k_matmul(u64* __restrict__ out, const u64* __restrict__ x, const i64* __restrict__ W, int K, int Nc,
-         int L, const int* __restrict__ skip_if_set) {
+         int L, const int* __restrict__ nnz /* tap count of W (null: always run) */) {
     extern __shared__ i64 s_w[];   // [K][MM_TN]
-    if (skip_if_set && *skip_if_set) return;          // the staged kernel took this matmul
+    if (nnz && 2L * *nnz <= (long)K * Nc) return;     // sparse weights: the tap-list kernel took this matmul
     const long m = blockIdx.x;
     const int n0 = blockIdx.y * MM_TN;
     for (int t = threadIdx.x; t < K * MM_TN; t += blockDim.x) {
@@ -238,80 +238,181 @@ struct MmTaps {            // scratch layout, one launch
     int* cnt;              // [Nc][3]  number of +1, -1, general taps
     unsigned short* kk;    // [Nc][K]  their k, grouped in that order
     i64* ww;               // [Nc][K]  weights (aligned with kk; only the general ones are read)
-    int* sparse;           // 1: k_matmul_taps runs, 0: k_matmul runs
+    int* nnz;              // non-zero weights: at most half of K*Nc -> k_matmul_taps runs, else k_matmul
 };
-__global__ void k_mm_taps(const i64* __restrict__ W, int K, int Nc, MmTaps t) {
-    __shared__ int s_nnz;
-    if (threadIdx.x == 0) s_nnz = 0;
-    __syncthreads();
-    int mine = 0;
-    for (int n = threadIdx.x; n < Nc; n += blockDim.x) {
-        unsigned short* kn = t.kk + (size_t)n * K;
-        i64* wn = t.ww + (size_t)n * K;
-        int c = 0, c0, c1;
-        for (int k = 0; k < K; k++) if (W[(size_t)k * Nc + n] == 1) kn[c++] = (unsigned short)k;
-        c0 = c;
-        for (int k = 0; k < K; k++) if (W[(size_t)k * Nc + n] == -1) kn[c++] = (unsigned short)k;
-        c1 = c;
-        for (int k = 0; k < K; k++) {
-            const i64 w = W[(size_t)k * Nc + n];
-            if (w != 0 && w != 1 && w != -1) { kn[c] = (unsigned short)k; wn[c] = w; c++; }
+// one warp per column: three ballot-compaction sweeps over k (+1, -1, general); the total tap count goes to *t.nnz
+// (zeroed by the host on the stream) and the consumers derive "sparse" from it
+__global__ void __launch_bounds__(256)
+k_mm_taps(const i64* __restrict__ W, int K, int Nc, MmTaps t) {
+    const int lane = threadIdx.x & 31;
+    const int n = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (n >= Nc) return;
+    unsigned short* kn = t.kk + (size_t)n * K;
+    i64* wn = t.ww + (size_t)n * K;
+    int c = 0;
+    for (int cls = 0; cls < 3; cls++) {
+        const int c_start = c;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const int k = k0 + lane;
+            const i64 w = (k < K) ? W[(size_t)k * Nc + n] : 0;
+            const int kind = (w == 1) ? 0 : (w == -1) ? 1 : 2;
+            const bool keep = w != 0 && kind == cls;
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int pos = c + __popc(mask & ((1u << lane) - 1u));
+                kn[pos] = (unsigned short)k;
+                wn[pos] = w;
+            }
+            c += __popc(mask);
         }
-        t.cnt[3 * n] = c0; t.cnt[3 * n + 1] = c1 - c0; t.cnt[3 * n + 2] = c - c1;
-        mine += c;
+        if (lane == 0) t.cnt[3 * n + cls] = c - c_start;
     }
-    atomicAdd(&s_nnz, mine);
-    __syncthreads();
-    if (threadIdx.x == 0) *t.sparse = (2L * s_nnz <= (long)K * Nc) ? 1 : 0;
+    if (lane == 0) atomicAdd(t.nnz, c);
+}
+__device__ __forceinline__ bool mm_sparse(const MmTaps& t, int K, int Nc) { return 2L * *t.nnz <= (long)K * Nc; }
+
+// persistent CTAs, `stages` operand tiles in flight: while the warps reduce tile i, the copy engine brings tiles
+// i+1 .. i+stages-1.  Each of the K rows of a tile is ONE bulk asynchronous copy (cp.async.bulk global -> shared, 16-byte
+// aligned middle of the row) counted on the stage's mbarrier, plus at most a head and a tail word moved by the issuing
+// thread: rows are L = k*N+1 words apart, so every other row starts 8 bytes off a 16-byte boundary.  A row keeps its
+// global 16-byte phase in shared memory (row stride MS_RS = MS_TC + 2 words, data at offset `phase`).
+#define MS_RS (MS_TC + 2)
+#define MM_NCW 8           // output columns per warp held in registers (Nc <= MM_NCW * 16 warps)
+__device__ __forceinline__ unsigned mm_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mm_stage_tile(u64* xt, u64* bar, const u64* __restrict__ x, long tile, int nchunk, int K, int L) {
+    const long m = tile / nchunk;
+    const int t0 = (int)(tile - m * nchunk) * MS_TC;
+    const int ncol = (L - t0 < MS_TC) ? L - t0 : MS_TC;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const u64* src = x + ((size_t)m * K + k) * L + t0;
+        const int ph = (int)(((uintptr_t)src >> 3) & 1);
+        u64* dst = xt + (size_t)k * MS_RS + ph;
+        const int head = ph ? 1 : 0;                                   // words before the first 16-byte boundary
+        const int mid = (ncol - head) & ~1;                            // words moved by the bulk copy
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mm_smem(bar)), "r"((unsigned)(mid * 8)) : "memory");
+        if (mid > 0)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(mm_smem(dst + head)), "l"(src + head), "r"((unsigned)(mid * 8)), "r"(mm_smem(bar)) : "memory");
+        // head / tail words: 8-byte asynchronous copies, their completion is this thread's second arrival on the barrier
+        // (nobody blocks on a global load while staging)
+        if (head && ncol > 0)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(mm_smem(dst)), "l"(src) : "memory");
+        if (head + mid < ncol)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(mm_smem(dst + head + mid)), "l"(src + head + mid) : "memory");
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(mm_smem(bar)) : "memory");
+        for (int c = ncol; c < MS_TC; c++) dst[c] = 0ULL;             // ragged last chunk of a row
+    }
 }
 
-__global__ void __launch_bounds__(256)
-k_matmul_taps(u64* __restrict__ out, const u64* __restrict__ x, int K, int Nc, int L, MmTaps t) {
+__global__ void __launch_bounds__(512)
+k_matmul_taps(u64* __restrict__ out, const u64* __restrict__ x, int K, int Nc, int L, long Mr, int stages, MmTaps t) {
     extern __shared__ __align__(16) unsigned char ms_raw[];
-    if (!*t.sparse) return;                               // dense weights: k_matmul takes this product
-    u64* xt = reinterpret_cast<u64*>(ms_raw);             // [K][MS_TC]
-    const long m = blockIdx.x;
-    const int t0 = blockIdx.y * MS_TC;
-    const u64* xm = x + (size_t)m * K * L + t0;
-    const int ncol = (L - t0 < MS_TC) ? L - t0 : MS_TC;
-    // stage the tile: consecutive threads copy consecutive words of a row (8-byte asynchronous copies, no registers)
-    for (int i = threadIdx.x; i < K * MS_TC; i += blockDim.x) {
-        const int k = i / MS_TC, c = i - k * MS_TC;
-        if (c < ncol) {
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(xt + i);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(xm + (size_t)k * L + c) : "memory");
-        } else
-            xt[i] = 0ULL;
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();
+    __shared__ __align__(8) u64 s_bar[4];
+    if (!mm_sparse(t, K, Nc)) return;                     // dense weights: k_matmul takes this product
+    u64* xs = reinterpret_cast<u64*>(ms_raw);             // [stages][K][MS_RS]
+    const size_t stage_words = (size_t)K * MS_RS;
+    const int nchunk = (L + MS_TC - 1) / MS_TC;
+    const long tiles = Mr * nchunk;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int n = warp; n < Nc; n += nwarps) {
-        const int cp = __ldg(t.cnt + 3 * n), cn = __ldg(t.cnt + 3 * n + 1), cg = __ldg(t.cnt + 3 * n + 2);
-        const unsigned short* kn = t.kk + (size_t)n * K;
-        const i64* wn = t.ww + (size_t)n * K;
-        u64 a0 = 0, a1 = 0, b0 = 0, b1 = 0;                // two word columns, two independent chains each
-        int j = 0;
-        for (; j + 1 < cp; j += 2) {
-            const u64* r0 = xt + (int)__ldg(kn + j) * MS_TC + lane;
-            const u64* r1 = xt + (int)__ldg(kn + j + 1) * MS_TC + lane;
-            a0 += r0[0]; a1 += r0[32]; b0 += r1[0]; b1 += r1[32];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; s++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mm_smem(&s_bar[s])), "r"(2 * K) : "memory");   // two arrivals per row
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // The CTA is persistent and a warp owns the same output columns (warp, warp + nwarps, ...) in every tile: the first
+    // 32 taps of each of its columns stay in registers for the whole kernel (lane l holds tap l)
+    int cnts[MM_NCW], kregs[MM_NCW];
+    i64 wregs[MM_NCW];
+#pragma unroll
+    for (int ci = 0; ci < MM_NCW; ci++) {
+        const int n = warp + ci * nwarps;
+        cnts[ci] = (n < Nc && lane < 3) ? __ldg(t.cnt + 3 * n + lane) : 0;
+        kregs[ci] = (n < Nc) ? (int)__ldg(t.kk + (size_t)n * K + (lane < K ? lane : 0)) : 0;
+        wregs[ci] = (n < Nc) ? __ldg(t.ww + (size_t)n * K + (lane < K ? lane : 0)) : 0;
+    }
+    // prologue: the first stages-1 tiles of this CTA
+    for (int s = 0; s < stages - 1; s++) {
+        const long tile = blockIdx.x + (long)s * gridDim.x;
+        if (tile < tiles) mm_stage_tile(xs + s * stage_words, &s_bar[s], x, tile, nchunk, K, L);
+    }
+    long it = 0;
+    for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
+        {
+            const long ahead = tile + (long)(stages - 1) * gridDim.x;
+            const int sa = (int)((it + stages - 1) % stages);
+            if (ahead < tiles || stages == 1) mm_stage_tile(xs + sa * stage_words, &s_bar[sa], x, stages == 1 ? tile : ahead, nchunk, K, L);
         }
-        if (j < cp) { const u64* r0 = xt + (int)__ldg(kn + j) * MS_TC + lane; a0 += r0[0]; a1 += r0[32]; j++; }
-        for (; j + 1 < cp + cn; j += 2) {
-            const u64* r0 = xt + (int)__ldg(kn + j) * MS_TC + lane;
-            const u64* r1 = xt + (int)__ldg(kn + j + 1) * MS_TC + lane;
-            a0 -= r0[0]; a1 -= r0[32]; b0 -= r1[0]; b1 -= r1[32];
+        const int sc = (int)(it % stages);
+        {
+            const unsigned parity = (unsigned)((it / stages) & 1);
+            asm volatile(
+                "{\n.reg .pred p;\nMMW_%=:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                "@p bra MMD_%=;\nbra MMW_%=;\nMMD_%=:\n}\n" ::"r"(mm_smem(&s_bar[sc])), "r"(parity) : "memory");
         }
-        if (j < cp + cn) { const u64* r0 = xt + (int)__ldg(kn + j) * MS_TC + lane; a0 -= r0[0]; a1 -= r0[32]; j++; }
-        for (; j < cp + cn + cg; j++) {
-            const u64 w = (u64)__ldg(wn + j);
-            const u64* r0 = xt + (int)__ldg(kn + j) * MS_TC + lane;
-            a0 += w * r0[0]; a1 += w * r0[32];
+        __syncthreads();                                   // head / tail words were written by ordinary stores
+        const u64* xt = xs + sc * stage_words;
+        const long m = tile / nchunk;
+        const int t0 = (int)(tile - m * nchunk) * MS_TC;
+        const int ncol = (L - t0 < MS_TC) ? L - t0 : MS_TC;
+        // 16-byte phase of row k of this tile: rows are L words apart
+        const size_t row0 = (size_t)m * K * L + t0;
+        const int ph0 = (int)((((uintptr_t)x >> 3) + row0) & 1), phstep = L & 1;
+        // Tap lists live in global memory (L2): lane l of the warp holds tap l of the column (one coalesced load per 32
+        // taps, requested one column ahead) and the loop broadcasts k / w with shuffles -- no dependent global load
+        // sits between two shared-memory reads.
+        // byte offset of row k inside the stage (row stride + its 16-byte phase), computed once per lane-held tap
+#define MM_OFF(kk_) (((kk_) * MS_RS + ((ph0 + (kk_) * phstep) & 1)) << 3)
+#define MM_ROW(off_) reinterpret_cast<const u64*>(xl + (off_))
+        const unsigned char* xl = reinterpret_cast<const unsigned char*>(xt + lane);
+#pragma unroll
+        for (int ci = 0; ci < MM_NCW; ci++) {
+            const int n = warp + ci * nwarps;
+            if (n >= Nc) break;
+            const int cp = __shfl_sync(0xffffffffu, cnts[ci], 0), cn = __shfl_sync(0xffffffffu, cnts[ci], 1),
+                      cg = __shfl_sync(0xffffffffu, cnts[ci], 2);
+            int oreg = MM_OFF(kregs[ci]);
+            i64 wreg = wregs[ci];
+            const unsigned short* kn = t.kk + (size_t)n * K;
+            const i64* wn = t.ww + (size_t)n * K;
+            const int total = cp + cn + cg;
+            u64 a0 = 0, a1 = 0, b0 = 0, b1 = 0;            // two word columns, two independent chains each
+            for (int base = 0; base < total; base += 32) {
+                if (base) {                                 // columns with more than 32 taps: further rounds from L2
+                    const int kk2 = (base + lane < total) ? (int)__ldg(kn + base + lane) : 0;
+                    oreg = MM_OFF(kk2);
+                    wreg = (base + lane < total) ? __ldg(wn + base + lane) : 0;
+                }
+                const int lim = (total - base < 32) ? total - base : 32;
+                int jj = 0;
+                const int e_pos = (cp - base < 0) ? 0 : (cp - base < lim ? cp - base : lim);            // +1 taps of this round
+                const int e_neg = (cp + cn - base < 0) ? 0 : (cp + cn - base < lim ? cp + cn - base : lim);
+                for (; jj + 1 < e_pos; jj += 2) {
+                    const u64* r0 = MM_ROW(__shfl_sync(0xffffffffu, oreg, jj));
+                    const u64* r1 = MM_ROW(__shfl_sync(0xffffffffu, oreg, jj + 1));
+                    a0 += r0[0]; a1 += r0[32]; b0 += r1[0]; b1 += r1[32];
+                }
+                if (jj < e_pos) { const u64* r0 = MM_ROW(__shfl_sync(0xffffffffu, oreg, jj)); a0 += r0[0]; a1 += r0[32]; jj++; }
+                for (; jj + 1 < e_neg; jj += 2) {
+                    const u64* r0 = MM_ROW(__shfl_sync(0xffffffffu, oreg, jj));
+                    const u64* r1 = MM_ROW(__shfl_sync(0xffffffffu, oreg, jj + 1));
+                    a0 -= r0[0]; a1 -= r0[32]; b0 -= r1[0]; b1 -= r1[32];
+                }
+                if (jj < e_neg) { const u64* r0 = MM_ROW(__shfl_sync(0xffffffffu, oreg, jj)); a0 -= r0[0]; a1 -= r0[32]; jj++; }
+                for (; jj < lim; jj++) {
+                    const u64 w = (u64)__shfl_sync(0xffffffffu, wreg, jj);
+                    const u64* r0 = MM_ROW(__shfl_sync(0xffffffffu, oreg, jj));
+                    a0 += w * r0[0]; a1 += w * r0[32];
+                }
+            }
+            u64* o = out + ((size_t)m * Nc + n) * L + t0;
+            if (lane < ncol) o[lane] = a0 + b0;
+            if (lane + 32 < ncol) o[lane + 32] = a1 + b1;
         }
-        u64* o = out + ((size_t)m * Nc + n) * L + t0;
-        if (lane < ncol) o[lane] = a0 + b0;
-        if (lane + 32 < ncol) o[lane + 32] = a1 + b1;
+#undef MM_ROW
+#undef MM_OFF
+        __syncthreads();                                   // the stage is overwritten by the copies of a later tile
     }
 }
 
@@ -431,27 +532,50 @@ int fhe_matmul_ct_clear(u64* out, const u64* x, const i64* W, long Mr, int K, in
     if (Mr == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem_dense = (size_t)K * MM_TN * sizeof(i64);
-    const size_t smem_taps = (size_t)K * MS_TC * 8;
+    const size_t smem_taps = (size_t)K * MS_RS * 8;
     if (smem_dense > 48 * 1024 || smem_taps > 200 * 1024)
         FHE_FAIL(3, "matmul_ct_clear: K=%d too large for the tiled kernels (use gather_mac)", K);
-    // which kernel runs is decided ON DEVICE by the density of W (no host synchronisation inside Server.run): both are
-    // enqueued and the one the flag rules out exits at once
     unsigned char* scratch = nullptr;
+    if (Nc > MM_NCW * 16) {
+        // more output columns than the tap-list kernel keeps in registers: the register-blocked kernel takes every W
+        k_matmul<<<dim3((unsigned)Mr, (Nc + MM_TN - 1) / MM_TN, col_chunks(L, 256)), 256, smem_dense, st>>>(out, x, W, K, Nc, L, nullptr);
+        FHE_CHECK_LAUNCH();
+        return 0;
+    }
+    // which kernel runs is decided ON DEVICE by the density of W (no host synchronisation inside Server.run): both are
+    // enqueued and the one the tap count rules out exits at once
     MmTaps t = {};
     const size_t b_cnt = ((size_t)Nc * 3 * sizeof(int) + 15) & ~(size_t)15;
     const size_t b_kk = ((size_t)Nc * K * sizeof(unsigned short) + 15) & ~(size_t)15;
     const size_t b_ww = (size_t)Nc * K * sizeof(i64);
-    FHE_CUDA(cudaMallocAsync(&scratch, b_cnt + b_kk + b_ww + 16, st));
+    FHE_CUDA(fhe_malloc_async(reinterpret_cast<void**>(&scratch), b_cnt + b_kk + b_ww + 16, st));
     t.cnt = reinterpret_cast<int*>(scratch);
     t.kk = reinterpret_cast<unsigned short*>(scratch + b_cnt);
     t.ww = reinterpret_cast<i64*>(scratch + b_cnt + b_kk);
-    t.sparse = reinterpret_cast<int*>(scratch + b_cnt + b_kk + b_ww);
-    k_mm_taps<<<1, 256, 0, st>>>(W, K, Nc, t);
+    t.nnz = reinterpret_cast<int*>(scratch + b_cnt + b_kk + b_ww);
+    FHE_CUDA(cudaMemsetAsync(t.nnz, 0, sizeof(int), st));
+    k_mm_taps<<<(unsigned)((Nc * 32 + 255) / 256), 256, 0, st>>>(W, K, Nc, t);
     FHE_CHECK_LAUNCH();
-    FHE_CUDA(cudaFuncSetAttribute(k_matmul_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_taps));
-    k_matmul_taps<<<dim3((unsigned)Mr, (unsigned)((L + MS_TC - 1) / MS_TC)), 256, smem_taps, st>>>(out, x, K, Nc, L, t);
-    FHE_CHECK_LAUNCH();
-    k_matmul<<<dim3((unsigned)Mr, (Nc + MM_TN - 1) / MM_TN, col_chunks(L, 256)), 256, smem_dense, st>>>(out, x, W, K, Nc, L, t.sparse);
+    {
+        // as many operand tiles in flight per CTA as shared memory holds (up to 4), persistent CTAs of 16 warps
+        const size_t stage = (size_t)K * MS_RS * 8;
+        int stages = (int)((200 * 1024) / stage);
+        stages = stages > 4 ? 4 : (stages < 1 ? 1 : stages);
+        const long tiles = Mr * (long)((L + MS_TC - 1) / MS_TC);
+        const int per_sm = (stage * stages <= 100 * 1024) ? 2 : 1;
+        long grid = (long)sm_count() * per_sm;
+        if (grid > tiles) grid = tiles;
+        static size_t smem_allowed[64] = {};              // per device: raise the opt-in limit only when it grows
+        int dev = 0;
+        FHE_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || smem_allowed[dev] < stage * stages) {
+            FHE_CUDA(cudaFuncSetAttribute(k_matmul_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(stage * stages)));
+            if (dev >= 0 && dev < 64) smem_allowed[dev] = stage * stages;
+        }
+        k_matmul_taps<<<(unsigned)grid, 512, stage * stages, st>>>(out, x, K, Nc, L, Mr, stages, t);
+        FHE_CHECK_LAUNCH();
+    }
+    k_matmul<<<dim3((unsigned)Mr, (Nc + MM_TN - 1) / MM_TN, col_chunks(L, 256)), 256, smem_dense, st>>>(out, x, W, K, Nc, L, t.nnz);
     FHE_CHECK_LAUNCH();
     if (scratch) FHE_CUDA(cudaFreeAsync(scratch, st));
     return 0;

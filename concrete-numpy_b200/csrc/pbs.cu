@@ -252,7 +252,7 @@ int fhe_bsk_relayout(double2* dst, const double2* src, int n, int k, int N, int 
     for (long t = 0; t < M; t++) map[plan_position(plans[fit[dst_variant]].meta, t)] = (int)inv_src[t];
     int* d_map = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
-    FHE_CUDA(cudaMallocAsync(&d_map, sizeof(int) * M, st));
+    FHE_CUDA(fhe_malloc_async(reinterpret_cast<void**>(&d_map), sizeof(int) * M, st));
     FHE_CUDA(cudaMemcpyAsync(d_map, map.data(), sizeof(int) * M, cudaMemcpyHostToDevice, st));
     FHE_CUDA(cudaStreamSynchronize(st));     // `map` is a host temporary
     const long nslices = (long)n * (k + 1) * level * (k + 1);

@@ -46,10 +46,10 @@ for n in range(64):
     W[rng.choice(128, 10, replace=False), n] = rng.choice([-1, 1], 10)
 Wd = torch.from_numpy(W).to(dev)
 report("cfg3_matmul_64x128x64_sparse_ternary", timed(lambda: E.matmul_ct_clear(x, Wd, 64, 128, 64, L)),
-       (64 * 128 + 64 * 64) * L * 8 + 128 * 64 * 8, "staged kernel, 10 non-zero weights per column")
+       (64 * 128 + 64 * 64) * L * 8 + 128 * 64 * 8, "tap-list kernel (x read once, bulk-copied tiles), 10 non-zero weights per column")
 Wfull = torch.from_numpy(rng.integers(-3, 4, (128, 64)).astype(np.int64)).to(dev)
 report("matmul_64x128x64_dense_weights", timed(lambda: E.matmul_ct_clear(x, Wfull, 64, 128, 64, L)),
-       (64 * 128 + 64 * 64) * L * 8 + 128 * 64 * 8, "same shape, dense weights: 4.3e9 u64 MACs -> INT-ALU bound")
+       (64 * 128 + 64 * 64) * L * 8 + 128 * 64 * 8, "same shape, dense weights: 4.3e9 u64 multiply-adds -> bound by the integer pipe (register-blocked kernel)")
 del x
 # cfg4: conv2d 1x8x28x28, 3x3, pad 1 (72 taps per output) through gather-MAC
 xin = rand_ct(8 * 28 * 28, L)
