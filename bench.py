@@ -229,7 +229,7 @@ class LinearTimer:
             return out
 
         def mm(x, W, Mr, K, Nc, L):
-            return timed("k_matmul", self._mm, (Mr * K + Mr * Nc) * L * 8 + K * Nc * 8, x, W, Mr, K, Nc, L)
+            return timed("k_matmul_taps (tap lists + dense fallback launch)", self._mm, (Mr * K + Mr * Nc) * L * 8 + K * Nc * 8, x, W, Mr, K, Nc, L)
 
         def gm(x, idx, w, L, bias=None):
             return timed("k_gather_mac", self._gm, (x.shape[0] + idx.shape[0]) * L * 8, x, idx, w, L, bias)
@@ -501,7 +501,7 @@ def run_ours(args):
                          "frac": achieved / fp64_peak if fp64_peak else None,
                          "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
                          "traffic_note": None if traffic is None else traffic.get("note"),
-                         "kernel": "k_pbs", "launches_timed": n_pbs_launch, "mean_launch_ms": pbs_ms / max(n_pbs_launch, 1),
+                         "kernel": "k_pbs_pipe", "launches_timed": n_pbs_launch, "mean_launch_ms": pbs_ms / max(n_pbs_launch, 1),
                          "ciphertexts_per_launch": pbs_cts / max(n_pbs_launch, 1),
                          "flops_per_pbs": fl, "share_of_step": pbs_ms / ms if ms else None,
                          "peak_source": "DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no fp64 entry)"},

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), "libfhe_b200.so")
-SOURCES = ["api.cu", "keys.cu", "keyswitch.cu", "keyswitch_tc.cu", "linear.cu", "pbs.cu", "pbs_inst_a.cu", "pbs_inst_b.cu", "pbs_inst_c.cu", "pbs_inst_d.cu"]
+SOURCES = ["api.cu", "keys.cu", "keyswitch.cu", "keyswitch_tc.cu", "linear.cu", "pbs.cu", "pbs_inst_a.cu", "pbs_inst_b.cu", "pbs_inst_c.cu", "pbs_inst_d.cu", "pbs_inst_e.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

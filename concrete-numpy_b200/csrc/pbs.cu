@@ -14,6 +14,7 @@ const PbsPlanEntry* pbs_plans_a(int* count);
 const PbsPlanEntry* pbs_plans_b(int* count);
 const PbsPlanEntry* pbs_plans_c(int* count);
 const PbsPlanEntry* pbs_plans_d(int* count);
+const PbsPlanEntry* pbs_plans_e(int* count);
 
 static std::vector<PbsPlanEntry> all_plans() {
     std::vector<PbsPlanEntry> v;
@@ -25,6 +26,8 @@ static std::vector<PbsPlanEntry> all_plans() {
     p = pbs_plans_a(&n);
     v.insert(v.end(), p, p + n);
     p = pbs_plans_d(&n);
+    v.insert(v.end(), p, p + n);
+    p = pbs_plans_e(&n);
     v.insert(v.end(), p, p + n);
     return v;
 }
@@ -67,6 +70,8 @@ static std::vector<int> fitting_plans(int N, int k, int level) {
             if (ctas < 1) ctas = 1;
             const long threads = ctas * m.NT;
             if (m.acctm && !use_acctm) continue;
+            // pipelined plans (acctm == 2) exist for what k_pbs_pipe runs: k = 1, two levels
+            if (m.acctm == 2 && !(k == 1 && level == 2)) continue;
             if (no_256x2 && m.C == 1 && m.NT == 256 && m.minb == 2) continue;
             // at equal residency the tensor-memory accumulator plan wins (profiles/r02_*: no remote loads in P1)
             const bool tie = (threads == best_threads) && best >= 0;

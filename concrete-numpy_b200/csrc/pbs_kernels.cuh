@@ -96,7 +96,7 @@ struct PbsPlan {
 
 struct PbsPlanMeta {       // what the host needs to know about a plan
     int C, logR1, lra, lrb, lrf, NT, minb, kmax, logM;
-    int acctm;             // accumulator in tensor memory + pushed rotated copy (PbsPlan::ACC_TM)
+    int acctm;             // 1: accumulator in tensor memory + pushed rotated copy (PbsPlan::ACC_TM), 2: and k_pbs_pipe
     long smem_fixed;       // bytes of shared memory besides ACC and the work buffers (twiddles live in TMEM)
 };
 
@@ -1277,7 +1277,7 @@ struct PbsLaunchArgs {
 template <class P>
 struct PbsPlanOps {
     static PbsPlanMeta meta() {
-        return PbsPlanMeta{P::C, P::LOGR1, P::LRA, P::LRB, P::LRF, P::NT, P::MINB, P::KMAX, P::LOGM, P::ACC_TM ? 1 : 0,
+        return PbsPlanMeta{P::C, P::LOGR1, P::LRA, P::LRB, P::LRF, P::NT, P::MINB, P::KMAX, P::LOGM, P::PIPE ? 2 : (P::ACC_TM ? 1 : 0),
                            (long)sizeof(double2) * P::TW_SMEM};
     }
     static size_t smem_pbs(const PbsGeom& g) {

@@ -1,4 +1,5 @@
-// Pipelined bootstrap for the large cluster plans (N = 32768 on 8 CTAs, k = 1, two decomposition levels).
+// Pipelined bootstrap for the cluster plans with 2048-point local transforms (N = 32768 on 8 CTAs, 16384 on 4, 8192 on
+// 2), k = 1, two decomposition levels.
 //
 // Same arithmetic, same Fourier key layout and same FFT factorisation as k_pbs with the accumulator in tensor memory
 // (PbsPlan::ACC_TM); what changes is how the three exchanges of a CMUX cross the cluster:
@@ -49,62 +50,73 @@ __device__ __forceinline__ u64 f2torus_frac(double x, double scale) {
     return ((u64)(((hi << 12) | (lo >> 20)) ^ 0x80000000u) << 32) | (u64)(lo << 12);
 }
 
-// 32-bit decomposition states of the 2*R1 coefficients of this thread's item of one polynomial:
-// closest representable of (X^a * ACC - ACC); the rotated operand was pushed into `rac` by its producers,
-// the thread's own words wait in its tensor-memory lane
+// A thread owns IPT = Q / NT items of every polynomial (item ii: q = tid + ii * NT); an item is the 2*R1 coefficients of one
+// stage-1 butterfly.  IPT * R1 = L1 / NT is the same for every plan with the same L1 and thread count (8 for L1 = 2048,
+// 256 threads): R1 = 8 -> one radix-8 item, R1 = 2 -> four radix-2 items, and the per-thread register / tensor-memory
+// footprint does not depend on the cluster size.
+//
+// 32-bit decomposition states of this thread's items of one polynomial: closest representable of (X^a * ACC - ACC); the
+// rotated operand was pushed into `rac` by its producers, the thread's own words wait in its tensor-memory lane
 template <class P>
-__device__ __forceinline__ void pipe_read_state(const u64* __restrict__ rac, unsigned tacc, int q, int nonrep,
-                                                unsigned* st) {
-    constexpr int R1 = P::R1;
+__device__ __forceinline__ void pipe_read_state(const u64* __restrict__ rac, unsigned tacc, int tid, int nonrep,
+                                                unsigned* st /* [IPT][2*R1] */) {
+    constexpr int R1 = P::R1, IPT = P::Q / P::NT;
+    unsigned ow[IPT * 4 * R1];
+    TmemIo<IPT * 4 * R1>::ld(tacc, ow);
+    u64 rv[IPT * 2 * R1];
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-        unsigned ow[2 * R1];
-        u64 rv[R1];
-        TmemIo<2 * R1>::ld(tacc + (unsigned)(half * 2 * R1), ow);
+    for (int ii = 0; ii < IPT; ii++)
 #pragma unroll
-        for (int e = 0; e < R1; e++) rv[e] = rac[((half * R1 + e) << P::LOGQ) + q];
-        tmem_wait_ld();
+        for (int hj = 0; hj < 2 * R1; hj++) rv[ii * 2 * R1 + hj] = rac[(hj << P::LOGQ) + tid + ii * P::NT];
+    tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < R1; e++) {
-            const u64 diff = rv[e] - (((u64)ow[2 * e + 1] << 32) | (u64)ow[2 * e]);
-            const unsigned top = (unsigned)(diff >> 32);
-            st[half * R1 + e] = ((top >> (unsigned)(nonrep - 33)) + 1u) >> 1;
-        }
+    for (int e = 0; e < IPT * 2 * R1; e++) {
+        const u64 diff = rv[e] - (((u64)ow[2 * e + 1] << 32) | (u64)ow[2 * e]);
+        const unsigned top = (unsigned)(diff >> 32);
+        st[e] = ((top >> (unsigned)(nonrep - 33)) + 1u) >> 1;
     }
 }
 
 // next digit of every state (least significant level first), fold + twist, radix-R1 butterfly, stage twiddle
 template <class P>
-__device__ __forceinline__ void pipe_emit_compute(unsigned* st, int base_log, const double2* T, const PbsGeom& g,
-                                                  double2* v) {
-    constexpr int R1 = P::R1;
+__device__ __forceinline__ void pipe_emit_compute(unsigned* st, int base_log, const double2* T /* [IPT][R1] */,
+                                                  const PbsGeom& g, double2* v /* [IPT][R1] */) {
+    constexpr int R1 = P::R1, IPT = P::Q / P::NT;
     const unsigned mask = (1u << base_log) - 1u;
-    double2 z[R1];
 #pragma unroll
-    for (int j1 = 0; j1 < R1; j1++) {
-        double d[2];
+    for (int ii = 0; ii < IPT; ii++) {
+        double2 z[R1];
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int hj = h * R1 + j1;
-            const unsigned res = st[hj] & mask;
-            const unsigned s2 = st[hj] >> base_log;
-            const unsigned carry = (((res - 1u) | s2) & res) >> (base_log - 1);
-            st[hj] = s2 + carry;
-            d[h] = i32_to_f64((int)res - (int)(carry << base_log));
+        for (int j1 = 0; j1 < R1; j1++) {
+            double d[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int e = ii * 2 * R1 + h * R1 + j1;
+                const unsigned res = st[e] & mask;
+                const unsigned s2 = st[e] >> base_log;
+                const unsigned carry = (((res - 1u) | s2) & res) >> (base_log - 1);
+                st[e] = s2 + carry;
+                d[h] = i32_to_f64((int)res - (int)(carry << base_log));
+            }
+            const double2 dd = make_double2(d[0], d[1]);
+            z[j1] = (j1 == 0) ? dd : cmul(dd, g.cj[j1]);
         }
-        const double2 dd = make_double2(d[0], d[1]);
-        z[j1] = (j1 == 0) ? dd : cmul(dd, g.cj[j1]);
-    }
-    Dft<R1, false>::run(z);
+        Dft<R1, false>::run(z);
 #pragma unroll
-    for (int t1 = 0; t1 < R1; t1++) v[t1] = cmul(z[t1], T[t1]);
+        for (int t1 = 0; t1 < R1; t1++) v[ii * R1 + t1] = cmul(z[t1], T[ii * R1 + t1]);
+    }
 }
 
 // chunk t1 of the staging buffer goes to CTA t1; inside the chunk the element sits where the receiver's swizzle wants it
 template <class P>
-__device__ __forceinline__ void pipe_stage(double2* __restrict__ stg, int off, const double2* v) {
+__device__ __forceinline__ void pipe_stage(double2* __restrict__ stg, int j2_0, const double2* v) {
+    constexpr int R1 = P::R1, IPT = P::Q / P::NT;
 #pragma unroll
-    for (int t1 = 0; t1 < P::R1; t1++) stg[(t1 << P::LOGQ) + off] = v[t1];
+    for (int ii = 0; ii < IPT; ii++) {
+        const int off = SW(j2_0 + ii * P::NT) & (P::Q - 1);
+#pragma unroll
+        for (int t1 = 0; t1 < R1; t1++) stg[(t1 << P::LOGQ) + off] = v[ii * R1 + t1];
+    }
 }
 
 // thread d < C: chunk d of `stg` -> chunk `rank` of work buffer `dst_buf` of CTA d, counted on its mbarrier `bar`
@@ -128,7 +140,9 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
     constexpr int C = P::C, R1 = P::R1, NT = P::NT, RF = P::RF, BUF = P::BUF, Q = P::Q, S = P::S;
     constexpr int N = P::N;
     constexpr int NG = BUF / RF;
-    static_assert(P::ACC_TM && P::TMEM_TW && C >= 2 && Q == NT && NG == NT, "pipelined bootstrap: one item per thread");
+    constexpr int IPT = Q / NT;               // items per thread and polynomial
+    static_assert(P::ACC_TM && P::TMEM_TW && C >= 2 && Q % NT == 0 && NG == NT && IPT * R1 * 4 <= 64,
+                  "pipelined bootstrap: whole items per thread, one fused-pass group per thread");
     static_assert(S * 8 == BUF * 16, "a rotated-accumulator half doubles as a staging buffer");
     constexpr unsigned BUF_BYTES = (unsigned)(sizeof(double2) << P::LOGBUF);
     const bool do_prof = (prof != nullptr) && blockIdx.x < 16 && threadIdx.x == 0;
@@ -161,19 +175,17 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
     cg::this_cluster().sync();                // every CTA's barriers exist before the first remote access
     cluster_arrive();                         // pairs with the wait of the first CMUX ("previous CMUX finished everywhere")
     unsigned ph = 0;
-    const int q = tid;
-    const int j2 = (rank << P::LOGQ) + q;
-    const int off = SW(j2) & (Q - 1);
-    // the R1 stage-1 twiddles of this thread's item never change: they live in the tensor-memory columns the plan leaves free
-    static_assert(2 * P::TM_THREAD + 2 * 4 * R1 <= 512 && P::TM_CTA == 512, "room for the stage-1 twiddles");
-    const unsigned tT = tw.base + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)(2 * P::TM_THREAD + (tid >> 7) * 4 * R1);
+    const int j2_0 = (rank << P::LOGQ) + tid;         // item ii of this thread: q = tid + ii * NT, j2 = j2_0 + ii * NT
+    // the stage-1 twiddles of this thread's items never change: they live in the tensor-memory columns the plan leaves free
+    static_assert(2 * P::TM_THREAD + 2 * 4 * IPT * R1 <= 512 && P::TM_CTA == 512, "room for the stage-1 twiddles");
+    const unsigned tT = tw.base + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)(2 * P::TM_THREAD + (tid >> 7) * 4 * IPT * R1);
     {
-        double2 T[R1];
-        load_T<P>(T, tw, j2);
-        tmem_store_c<R1>(tT, T);
+        double2 T[IPT * R1];
+#pragma unroll
+        for (int ii = 0; ii < IPT; ii++) load_T<P>(T + ii * R1, tw, j2_0 + ii * NT);
+        tmem_store_c<IPT * R1>(tT, T);
         tmem_wait_st();
     }
-
     for (long ct = cluster_id; ct < B; ct += nclusters) {
         const u64* lwe = in + (size_t)ct * (g.n + 1);
         const u64* lut = luts + (size_t)(lut_idx ? lut_idx[ct] : 0) * 2 * N;
@@ -191,16 +203,18 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
             }
 #pragma unroll 1
             for (int c = 0; c < 2; c++) {
-                unsigned ow[4 * R1];
+                unsigned ow[IPT * 4 * R1];
 #pragma unroll
-                for (int hj = 0; hj < 2 * R1; hj++) {
-                    const int v = ((hj << P::LOGL1) + j2 - a0) & (2 * N - 1);
-                    u64 x = lut[(size_t)c * N + (v & (N - 1))];
-                    if (v >> (P::LOGM + 1)) x = 0ULL - x;
-                    ow[2 * hj] = (unsigned)x;
-                    ow[2 * hj + 1] = (unsigned)(x >> 32);
-                }
-                TmemIo<4 * R1>::st(tw.tAcc + (unsigned)(c * 4 * R1), ow);
+                for (int ii = 0; ii < IPT; ii++)
+#pragma unroll
+                    for (int hj = 0; hj < 2 * R1; hj++) {
+                        const int v = ((hj << P::LOGL1) + j2_0 + ii * NT - a0) & (2 * N - 1);
+                        u64 x = lut[(size_t)c * N + (v & (N - 1))];
+                        if (v >> (P::LOGM + 1)) x = 0ULL - x;
+                        ow[(ii * 2 * R1 + hj) * 2] = (unsigned)x;
+                        ow[(ii * 2 * R1 + hj) * 2 + 1] = (unsigned)(x >> 32);
+                    }
+                TmemIo<IPT * 4 * R1>::st(tw.tAcc + (unsigned)(c * IPT * 4 * R1), ow);
             }
             tmem_wait_st();
         }
@@ -219,19 +233,19 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 prefetch_l2_bulk(bskF + (size_t)(i + 1) * ggsw_stride + (((size_t)tid * C + rank) << P::LOGBUF), BUF_BYTES);
             // ---------------- P1: decompose X^a * ACC - ACC, stage 1, bulk copies to the owners
             {
-                double2 T[R1];
-                tmem_load_c<R1>(tT, T);
-                unsigned st[2 * R1];
-                double2 v[R1];
+                double2 T[IPT * R1];
+                tmem_load_c<IPT * R1>(tT, T);
+                unsigned st[IPT * 2 * R1];
+                double2 v[IPT * R1];
                 // polynomial 0
                 mbar_wait(&s_bar[6], ph);
                 PIPE_PROF(7)
                 if (tid == 0 && push) mbar_arm(&s_bar[6], BUF_BYTES);
-                pipe_read_state<P>(ra, tw.tAcc, q, nonrep, st);
+                pipe_read_state<P>(ra, tw.tAcc, tid, nonrep, st);
                 __syncthreads();                                   // rotated polynomial 0 consumed: its half stages (0, lv 0)
                 PIPE_PROF(9)
                 pipe_emit_compute<P>(st, base_log, T, g, v);       // level index 1 (least significant digits)
-                pipe_stage<P>(xstg, off, v);
+                pipe_stage<P>(xstg, j2_0, v);
                 fence_proxy_async();                 // every writer: its staged values must be visible to the copy engine
                 __syncthreads();
                 // nothing of this CMUX may reach a peer that has not finished the previous one (it still reads its spare
@@ -240,7 +254,7 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 if (tid < C) pipe_send<P>(xstg, work + 2 * (size_t)BUF, &s_bar[2], rank, tid, g.dbg & 2);
                 PIPE_PROF(10)
                 pipe_emit_compute<P>(st, base_log, T, g, v);       // level index 0
-                pipe_stage<P>(reinterpret_cast<double2*>(ra), off, v);
+                pipe_stage<P>(reinterpret_cast<double2*>(ra), j2_0, v);
                 fence_proxy_async();                 // every writer: its staged values must be visible to the copy engine
                 __syncthreads();
                 if (tid < C) pipe_send<P>(reinterpret_cast<double2*>(ra), work, &s_bar[0], rank, tid, g.dbg & 2);
@@ -249,10 +263,10 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 mbar_wait(&s_bar[7], ph);
                 PIPE_PROF(12)
                 if (tid == 0 && push) mbar_arm(&s_bar[7], BUF_BYTES);
-                pipe_read_state<P>(ra + S, tw.tAcc + (unsigned)(4 * R1), q, nonrep, st);
+                pipe_read_state<P>(ra + S, tw.tAcc + (unsigned)(IPT * 4 * R1), tid, nonrep, st);
                 __syncthreads();
                 pipe_emit_compute<P>(st, base_log, T, g, v);
-                pipe_stage<P>(reinterpret_cast<double2*>(ra + S), off, v);
+                pipe_stage<P>(reinterpret_cast<double2*>(ra + S), j2_0, v);
                 fence_proxy_async();                 // every writer: its staged values must be visible to the copy engine
                 __syncthreads();
                 if (tid < C) pipe_send<P>(reinterpret_cast<double2*>(ra + S), work + 3 * (size_t)BUF, &s_bar[3], rank, tid, g.dbg & 2);
@@ -264,7 +278,7 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 pipe_emit_compute<P>(st, base_log, T, g, v);
                 cluster_wait();
                 PIPE_PROF(15)
-                pipe_stage<P>(xstg, off, v);
+                pipe_stage<P>(xstg, j2_0, v);
                 fence_proxy_async();                 // every writer: its staged values must be visible to the copy engine
                 __syncthreads();
                 if (tid < C) pipe_send<P>(xstg, work + (size_t)BUF, &s_bar[1], rank, tid, g.dbg & 2);
@@ -350,41 +364,44 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
             PIPE_PROF(5)
             // ---------------- P5: inverse radix-R1 stage, untwist, round, ACC += ; push X^{a'} * ACC to its readers
             {
-                double2 T[R1];
-                tmem_load_c<R1>(tT, T);
-                const int u = j2 + (a_next & (P::L1 - 1));
-                const int j2d = u & (P::L1 - 1);
-                const int hbd = (a_next >> P::LOGL1) + (u >> P::LOGL1);
-                const int dcta = (g.dbg & 1) ? rank : (j2d >> P::LOGQ);
+                double2 T[IPT * R1];
+                tmem_load_c<IPT * R1>(tT, T);
 #pragma unroll 1
                 for (int o = 0; o < 2; o++) {
                     mbar_wait(&s_bar[4 + o], ph);
                     if (tid == 0) mbar_arm(&s_bar[4 + o], BUF_BYTES);          // next CMUX
-                    double2 z[R1];
-                    stage1_gather_local<P>(work + ((size_t)(2 + o) << P::LOGBUF), j2, T, g, z);
-                    const unsigned dst = mapa_u32(smem_u32(ra + (size_t)o * S + (j2d & (Q - 1))), dcta);
-                    const unsigned dbar = mapa_u32(smem_u32(&s_bar[6 + o]), dcta);
+                    const unsigned ta = tw.tAcc + (unsigned)(o * IPT * 4 * R1);
+                    unsigned ow[IPT * 4 * R1];
+                    TmemIo<IPT * 4 * R1>::ld(ta, ow);
+                    tmem_wait_ld();
 #pragma unroll
-                    for (int half = 0; half < 2; half++) {
-                        unsigned ow[2 * R1];
-                        const unsigned ta = tw.tAcc + (unsigned)(o * 4 * R1 + half * 2 * R1);
-                        TmemIo<2 * R1>::ld(ta, ow);
-                        tmem_wait_ld();
+                    for (int ii = 0; ii < IPT; ii++) {
+                        const int j2 = j2_0 + ii * NT;
+                        double2 z[R1];
+                        stage1_gather_local<P>(work + ((size_t)(2 + o) << P::LOGBUF), j2, T + ii * R1, g, z);
+                        // coefficient p = hj*L1 + j2 lands on (p + a') mod N, negated when it wraps once
+                        const int u = j2 + (a_next & (P::L1 - 1));
+                        const int j2d = u & (P::L1 - 1);
+                        const int hbd = (a_next >> P::LOGL1) + (u >> P::LOGL1);
+                        const int dcta = (g.dbg & 1) ? rank : (j2d >> P::LOGQ);
+                        const unsigned dst = mapa_u32(smem_u32(ra + (size_t)o * S + (j2d & (Q - 1))), dcta);
+                        const unsigned dbar = mapa_u32(smem_u32(&s_bar[6 + o]), dcta);
 #pragma unroll
-                        for (int j1 = 0; j1 < R1; j1++) {
-                            const u64 v = (((u64)ow[2 * j1 + 1] << 32) | (u64)ow[2 * j1]) +
-                                          f2torus_frac(half ? z[j1].y : z[j1].x, tscale);
-                            ow[2 * j1] = (unsigned)v;
-                            ow[2 * j1 + 1] = (unsigned)(v >> 32);
+                        for (int hj = 0; hj < 2 * R1; hj++) {
+                            const int e = ii * 2 * R1 + hj;
+                            const int j1 = hj & (R1 - 1);
+                            const u64 v = (((u64)ow[2 * e + 1] << 32) | (u64)ow[2 * e]) +
+                                          f2torus_frac((hj >= R1) ? z[j1].y : z[j1].x, tscale);
+                            ow[2 * e] = (unsigned)v;
+                            ow[2 * e + 1] = (unsigned)(v >> 32);
                             if (push) {
-                                // coefficient p = hj*L1 + j2 lands on (p + a') mod N, negated when it wraps once
-                                const int bt = (half * R1 + j1 + hbd) & (4 * R1 - 1);
+                                const int bt = (hj + hbd) & (4 * R1 - 1);
                                 st_async_u64(dst + ((unsigned)(bt & (2 * R1 - 1)) << (P::LOGQ + 3)),
                                              (bt >> (P::LOGR1 + 1)) ? (0ULL - v) : v, dbar);
                             }
                         }
-                        TmemIo<2 * R1>::st(ta, ow);
                     }
+                    TmemIo<IPT * 4 * R1>::st(ta, ow);
                 }
                 tmem_wait_st();
             }
@@ -397,19 +414,22 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
             u64* o = out + (size_t)ct * ((size_t)N + 1);
 #pragma unroll 1
             for (int c = 0; c < 2; c++) {
-                unsigned ow[4 * R1];
-                TmemIo<4 * R1>::ld(tw.tAcc + (unsigned)(c * 4 * R1), ow);
+                unsigned ow[IPT * 4 * R1];
+                TmemIo<IPT * 4 * R1>::ld(tw.tAcc + (unsigned)(c * IPT * 4 * R1), ow);
                 tmem_wait_ld();
 #pragma unroll
-                for (int hj = 0; hj < 2 * R1; hj++) {
-                    const int j = (hj << P::LOGL1) + j2;
-                    const u64 v = ((u64)ow[2 * hj + 1] << 32) | (u64)ow[2 * hj];
-                    if (c == 0) {
-                        if (j == 0) o[0] = v;
-                        else o[N - j] = 0ULL - v;
-                    } else if (j == 0)
-                        o[N] = v;
-                }
+                for (int ii = 0; ii < IPT; ii++)
+#pragma unroll
+                    for (int hj = 0; hj < 2 * R1; hj++) {
+                        const int j = (hj << P::LOGL1) + j2_0 + ii * NT;
+                        const int e = ii * 2 * R1 + hj;
+                        const u64 v = ((u64)ow[2 * e + 1] << 32) | (u64)ow[2 * e];
+                        if (c == 0) {
+                            if (j == 0) o[0] = v;
+                            else o[N - j] = 0ULL - v;
+                        } else if (j == 0)
+                            o[N] = v;
+                    }
             }
         }
         PIPE_PROF(8)
