@@ -399,11 +399,128 @@ def linear_wide():
          [np.full((8,), 100000), rng.integers(0, 100001, (8,))])
 
 
+def sweep():
+    """Full parameterisations of the reference's operator tests, read from the reference itself: the test modules under
+    /root/reference/tests/execution are imported and the argument lists of their `pytest.mark.parametrize` decorators are
+    iterated, so the functions, shapes, ranges and encryption statuses below are the reference's own objects (nothing is
+    restated here).  Covers test_comparison.py, test_shift.py, test_bitwise.py, test_matmul.py, test_sum.py,
+    test_static_indexing.py and test_static_assignment.py."""
+    import importlib.util
+    import itertools
+
+    rng = np.random.default_rng(2024)
+    np.random.seed(2024)                      # the assignment cases draw their constants at import time
+
+    def load(name):
+        path = os.path.join(ref_frontend.REFERENCE, "tests", "execution", name + ".py")
+        spec = importlib.util.spec_from_file_location("ref_tests_" + name, path)
+        module = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(module)
+        return module
+
+    def grid(test_function):
+        """[{argname: value}] for the cartesian product of the test's parametrize marks"""
+        axes = []
+        for mark in reversed(test_function.pytestmark):
+            if mark.name != "parametrize":
+                continue
+            names = [n.strip() for n in mark.args[0].split(",")]
+            rows = []
+            for item in mark.args[1]:
+                if type(item).__name__ == "ParameterSet":        # pytest.param(...)
+                    values = item.values
+                else:
+                    values = (item,) if len(names) == 1 else item
+                rows.append(dict(zip(names, values)))
+            axes.append(rows)
+        for combo in itertools.product(*axes):
+            merged = {}
+            for part in combo:
+                merged.update(part)
+            yield merged
+
+    def draw(spec, mode=None):
+        lo, hi = spec["range"]
+        shape = spec.get("shape", ())
+        if mode == "min":
+            return np.full(shape, lo) if shape != () else lo
+        if mode == "max":
+            return np.full(shape, hi) if shape != () else hi
+        return _rand(rng, lo, hi, shape)
+
+    def from_parameters(name, function, parameters, extra_samples=()):
+        names = list(parameters)
+        statuses = {k: parameters[k]["status"] for k in names}
+
+        def sample(mode=None):
+            vals = tuple(draw(parameters[k], mode) for k in names)
+            return vals if len(vals) > 1 else vals[0]
+
+        inputset = [sample() for _ in range(60)] + [sample("min"), sample("max")]
+        emit(name, function, statuses, inputset, [sample(), sample()] + list(extra_samples))
+
+    only = os.environ.get("GOLDEN_ONLY")
+
+    def wanted(name):
+        return only is None or only in name
+
+    comparison = load("test_comparison")
+    for i, row in enumerate(grid(comparison.test_comparison)):
+        if wanted("cmp"):
+            from_parameters(f"sw_cmp_{i:02d}", row["function"], row["parameters"])
+    for i, row in enumerate(grid(comparison.test_optimized_comparison)):
+        if wanted("cmpopt"):
+            from_parameters(f"sw_cmpopt_{i:02d}", row["function"], row["parameters"])
+    shift = load("test_shift")
+    for i, row in enumerate(grid(shift.test_left_shift)):
+        if wanted("shl"):
+            extra = [(a, b) for a in range(2) for b in range(8)] if i == 0 else []     # test_left_shift_coverage
+            from_parameters(f"sw_shl_{i:02d}", row["function"], row["parameters"], extra)
+    for i, row in enumerate(grid(shift.test_right_shift)):
+        if wanted("shr"):
+            extra = [(0b11, 0), (0b11, 1), (0b110, 2), (0b1100, 3), (0b11000, 4), (0b110000, 5)] if i == 0 else []
+            from_parameters(f"sw_shr_{i:02d}", row["function"], row["parameters"], extra)
+    bitwise = load("test_bitwise")
+    for i, row in enumerate(grid(bitwise.test_bitwise)):
+        if wanted("bit"):
+            from_parameters(f"sw_bit_{i:02d}", row["function"], row["parameters"])
+    matmul = load("test_matmul")
+    for i, row in enumerate(grid(matmul.test_matmul)):
+        if not wanted("mm"):
+            continue
+        lhs_shape, rhs_shape, (lo, hi) = row["lhs_shape"], row["rhs_shape"], row["bounds"]
+        lhs_cst, rhs_cst = rng.integers(lo, hi, lhs_shape), rng.integers(lo, hi, rhs_shape)
+        emit(f"sw_mm_{i:02d}_enc_cst", lambda x: x @ rhs_cst, {"x": "encrypted"},
+             [rng.integers(lo, hi, lhs_shape) for _ in range(40)] + [np.full(lhs_shape, hi - 1), np.full(lhs_shape, lo)],
+             [rng.integers(lo, hi, lhs_shape)])
+        emit(f"sw_mm_{i:02d}_cst_enc", lambda x: lhs_cst @ x, {"x": "encrypted"},
+             [rng.integers(lo, hi, rhs_shape) for _ in range(40)] + [np.full(rhs_shape, hi - 1), np.full(rhs_shape, lo)],
+             [rng.integers(lo, hi, rhs_shape)])
+    summation = load("test_sum")
+    for i, row in enumerate(grid(summation.test_sum)):
+        if wanted("sum"):
+            from_parameters(f"sw_sum_{i:02d}", row["function"], row["parameters"])
+    indexing = load("test_static_indexing")
+    for i, row in enumerate(grid(indexing.test_static_indexing)):
+        if wanted("idx"):
+            shape = row["shape"]
+            emit(f"sw_idx_{i:02d}", row["function"], {"x": "encrypted"},
+                 [rng.integers(0, 2 ** 5, shape) for _ in range(40)] + [np.zeros(shape, dtype=np.int64), np.full(shape, 31)],
+                 [rng.integers(0, 2 ** 5, shape)])
+    assignment = load("test_static_assignment")
+    for i, row in enumerate(grid(assignment.test_static_assignment)):
+        if wanted("asg"):
+            shape = row["shape"]
+            emit(f"sw_asg_{i:02d}", row["function"], {"x": "encrypted"},
+                 [rng.integers(0, 2 ** 7, shape) for _ in range(40)] + [np.zeros(shape, dtype=np.int64), np.full(shape, 127)],
+                 [rng.integers(0, 2 ** 7, shape)])
+
+
 GROUPS = {"lin": linear_wide, "cfg3b": cfg3b, "wide": wide, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "ops": ops, "ka": known_answers,
-          "cfg5small": lambda: cfg5(8)}
+          "cfg5small": lambda: cfg5(8), "sweep": sweep}
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    wanted = sys.argv[1:] or [g for g in GROUPS if g != "cfg5small"] + ["cfg5small"]
+    wanted = sys.argv[1:] or [g for g in GROUPS if g not in ("cfg5small", "sweep")] + ["cfg5small", "sweep"]
     for g in wanted:
         GROUPS[g]()

@@ -17,6 +17,9 @@ from golden_util import golden_names, load_golden, same, to_value
 os.environ.setdefault("CNP_B200_KEY_SEED", "20261019")
 
 FAST = [n for n in golden_names() if n.startswith(("ops_", "ka_", "lin_", "cfg5_kvdb8", "cfg1", "cfg3"))]
+# full parameterisations of the reference's comparison / shift / bitwise / matmul / sum / static indexing / static
+# assignment tests, generated from the reference's own parametrize lists (oracle/gen_golden.py: sweep)
+SWEEP = [n for n in golden_names() if n.startswith("sw_")]
 HEAVY = [n for n in golden_names() if n.startswith(("cfg2", "cfg4", "cfg5_kvdb128"))]
 
 
@@ -35,6 +38,11 @@ def check(name):
 
 @pytest.mark.parametrize("name", FAST)
 def test_golden_encrypted_execution(cuda_device, name):
+    check(name)
+
+
+@pytest.mark.parametrize("name", SWEEP)
+def test_golden_reference_parameter_sweep(cuda_device, name):
     check(name)
 
 

@@ -69,6 +69,35 @@ def test_selected_parameters_error_rate(cuda_device, bits):
     assert meas < model + 1.0, (meas, model)
 
 
+def test_empirical_error_rate_resolves_the_optimizer_target(cuda_device):
+    """north_star: "an empirical error rate at or below the optimizer's p_error".  A 1e-6 target cannot be resolved by
+    any affordable sample, so the parameters are searched for p_error = 1e-3 and 2^18 chained lookups are run (the model
+    describes a lookup whose input is a bootstrap output): the error count must stay below the binomial 4-sigma bound at
+    the target, and -- so that the test would notice a noise model that is far too pessimistic or a kernel that is too
+    quiet to be measuring anything -- above a tenth of the modelled rate."""
+    bits, target, total, B = 4, 1e-3, 1 << 18, 1 << 15
+    p = P.select_parameters(bits, 1.0, target)
+    model = P.estimate_p_error(p, 1.0)
+    assert model <= target
+    ks = E.KeySet(p, cuda_device, seed=17)
+    ev = E.EvalKeys.of(ks)
+    rng = np.random.default_rng(0)
+    table = rng.integers(0, 1 << bits, (1, 1 << bits))
+    luts = E.from_np_u64(E.build_lut_accumulators(p, table), cuda_device)
+    ident = E.from_np_u64(E.build_lut_accumulators(p, np.arange(1 << bits)[None, :]), cuda_device)
+    errors = 0
+    for _ in range(total // B):
+        m = rng.integers(0, 1 << bits, B).astype(np.uint64)
+        first = E.table_lookup(ev, E.encrypt(ks, m), luts)
+        exp = table[0, m.astype(np.int64)].astype(np.uint64)
+        good = E.decrypt(ks, first) == exp
+        second = E.decrypt(ks, E.table_lookup(ev, first, ident))
+        errors += int((second[good] != exp[good]).sum())
+    bound = total * target + 4.0 * math.sqrt(total * target)
+    assert errors <= bound, (errors, bound, model)
+    assert errors >= 0.1 * model * total, (errors, model)
+
+
 @pytest.mark.parametrize("bits", [9, 16])
 def test_wide_lookup_noise_within_model_and_error_free(cuda_device, bits):
     """Wide (CRT) lookups at the searched 128-bit parameters: every result exact, and the measured output noise of the
