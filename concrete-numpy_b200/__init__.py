@@ -6,7 +6,7 @@ Layout:
   csrc/            hand-written sm_100a CUDA kernels + the C ABI (include/fhe_b200.h)
   _lib.py          ctypes binding of libfhe_b200.so (fails loudly when the library is missing)
   params.py        crypto-parameter selection + noise model (stands in for concrete-optimizer)
-  keys.py          device-resident key sets, encrypt / decrypt
+  engine.py        device-resident key sets, encrypt / decrypt, keyswitch / bootstrap / linear-op launches
   mlir_text/       FHE / FHELinalg MLIR text: builder shim (`mlir`, `concrete.lang`) and parser
   wide.py          9..16-bit values: CRT residues, bit extraction, circuit bootstrapping, vertical packing
   executor.py      walks the parsed program and launches the kernels
