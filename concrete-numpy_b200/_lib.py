@@ -46,6 +46,7 @@ _SIGS = {
     "fhe_cmux_batch": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_blind_rotate_batch": (C.c_int, [_p, _p, C.c_long, _p, C.c_long, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_pbs_set_profile": (C.c_int, [_p]),
+    "fhe_pbs_set_pipeline": (C.c_int, [C.c_int]),
     "fhe_debug_polymul": (C.c_int, [_p, _p, _p, C.c_long, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_lin_add": (C.c_int, [_p, _p, _p, _p, _p, C.c_long, C.c_int, _p]),
     "fhe_lin_sub": (C.c_int, [_p, _p, _p, _p, _p, C.c_long, C.c_int, _p]),

@@ -175,6 +175,7 @@ static int get_plan(int n, int k, int N, int level, int base_log, int variant, c
 }
 
 static long long* g_prof_buf = nullptr;
+int g_pbs_pipeline = [] { const char* e = getenv("FHE_PBS_PIPE"); return (e && e[0] == '0') ? 0 : 1; }();
 
 // position of natural frequency t of the M-point spectrum inside one (j, o) slice [C][RF][BUF/RF] of a plan
 static long plan_position(const PbsPlanMeta& m, long t) {
@@ -203,6 +204,14 @@ extern "C" {
 int fhe_pbs_set_profile(long long* dev_buf) {
     g_prof_buf = dev_buf;
     return 0;
+}
+
+// test / measurement hook: 0 makes the pipelined plans run their generic kernel (k_pbs) instead of k_pbs_pipe; returns
+// the previous setting.  The two kernels are bit-identical by construction (tests/test_gpu_kernels.py).
+int fhe_pbs_set_pipeline(int enabled) {
+    const int prev = g_pbs_pipeline;
+    g_pbs_pipeline = enabled ? 1 : 0;
+    return prev;
 }
 
 // cluster size (CTAs per ciphertext) the on-chip layout uses for these parameters, <0 if unsupported

@@ -286,6 +286,19 @@ __device__ __forceinline__ u64 f2torus(double x) {
     if (lo_d >= 2147483648.0) res += 1ULL << 32;                    // lo == +2^31 wrapped to -2^31
     return res;
 }
+// x * scale (scale = 2^-64 / M) -> torus word: the fractional part of the scaled value, read straight out of the mantissa
+// of (frac + 1.5) in [1, 2].  5 FP64 + 3 integer operations instead of the 10 + 6 of f2torus; the result is rounded to a
+// multiple of 2^12 (2^-52 of the torus), 2^28 times below the fp64 FFT's own error at these sizes.
+__device__ __forceinline__ u64 f2torus_frac(double x, double scale) {
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
+    const double y = x * scale;
+    const double f = y - ((y + MAGIC) - MAGIC);              // y - rint(y) in [-0.5, 0.5], exact
+    const double t = f + 1.5;
+    const unsigned hi = (unsigned)__double2hiint(t), lo = (unsigned)__double2loint(t);
+    // mantissa << 12 (sign and exponent fall off the top), minus 2^63
+    return ((u64)(((hi << 12) | (lo >> 20)) ^ 0x80000000u) << 32) | (u64)(lo << 12);
+}
+
 __device__ __forceinline__ u64 f2torus_ref(double x) {
 
     x -= 18446744073709551616.0 * rint(x * 5.42101086242752217e-20);
@@ -372,16 +385,18 @@ __device__ __forceinline__ void tw_teardown(const TwCtx& tw) {
 template <int LR, int LOGLC, int LOGBUF, int NT, bool INV, bool TM>
 __device__ __forceinline__ void mid_pass(double2* __restrict__ work, int nbuf, unsigned tw_taddr /* TMEM */,
                                          const double2* __restrict__ tw /* shared: [(R-1)][S] */,
-                                         int bstep = 1 /* distance between the buffers, in buffers */) {
+                                         int bstep = 1 /* distance between the buffers, in buffers */,
+                                         int tix = -1 /* thread index inside the NT threads running the pass (default: threadIdx.x) */) {
     constexpr int R = 1 << LR;
     constexpr int LOGSS = LOGLC - LR, SS = 1 << LOGSS;          // stride inside a sub-transform
     constexpr int NBF = 1 << (LOGBUF - LR);                     // butterflies per buffer
     constexpr int WPT = (NBF >= NT) ? NBF / NT : 1;             // butterfly indices per thread
     constexpr int GROUPS = (NBF >= NT) ? 1 : NT / NBF;          // thread groups sharing the buffers
-    const int grp = (GROUPS > 1) ? (int)(threadIdx.x / NBF) : 0;
+    const int tx = (tix < 0) ? (int)threadIdx.x : tix;
+    const int grp = (GROUPS > 1) ? (tx / NBF) : 0;
 #pragma unroll 1
     for (int it = 0; it < WPT; it++) {
-        const int w = (GROUPS > 1) ? (int)(threadIdx.x % NBF) : (int)threadIdx.x + it * NT;
+        const int w = (GROUPS > 1) ? (tx % NBF) : tx + it * NT;
         const int b = w >> LOGSS, q = w & (SS - 1);
         const int pos0 = (b << LOGLC) + q;
         // the R-1 twiddles W_Lc^{q m} of this thread's butterfly index live in its tensor-memory lane
@@ -653,6 +668,7 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
     if (C > 1) rank = (int)cg::this_cluster().block_rank();
     const long cluster_id = blockIdx.x / C, nclusters = gridDim.x / C;
     const size_t ggsw_stride = (size_t)J * (k + 1) * C * BUF;   // double2 per CMUX iteration
+    const double tscale = g.inv_M * 5.42101086242752217e-20;    // 2^-64 / M (f2torus_frac)
 
     const TwCtx tw = tw_setup<P>(work + (size_t)J * BUF, twT, tw_mid);
     // cluster plans with at least k+1 spare work buffers (level >= 2): the inverse exchange is pushed with
@@ -880,7 +896,7 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
 #pragma unroll
                         for (int j1 = 0; j1 < R1; j1++) {
                             const u64 v = (((u64)ow[2 * j1 + 1] << 32) | (u64)ow[2 * j1]) +
-                                          f2torus((half ? z[j1].y : z[j1].x) * g.inv_M);
+                                          f2torus_frac(half ? z[j1].y : z[j1].x, tscale);
                             ow[2 * j1] = (unsigned)v;
                             ow[2 * j1 + 1] = (unsigned)(v >> 32);
                             if (push) {
@@ -894,8 +910,8 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
                 } else {
 #pragma unroll
                     for (int j1 = 0; j1 < R1; j1++) {
-                        acco[(j1 << P::LOGQ) + q] += f2torus(z[j1].x * g.inv_M);
-                        acco[((R1 + j1) << P::LOGQ) + q] += f2torus(z[j1].y * g.inv_M);
+                        acco[(j1 << P::LOGQ) + q] += f2torus_frac(z[j1].x, tscale);
+                        acco[((R1 + j1) << P::LOGQ) + q] += f2torus_frac(z[j1].y, tscale);
                     }
                 }
             }
@@ -1110,6 +1126,7 @@ k_cmux(u64* __restrict__ out, const u64* __restrict__ pool, const int* __restric
     const long cluster_id = blockIdx.x / C, nclusters = gridDim.x / C;
     const size_t glwe = (size_t)(k + 1) * N;
     const size_t ggsw_stride = (size_t)J * (k + 1) * C * BUF;
+    const double tscale = g.inv_M * 5.42101086242752217e-20; // 2^-64 / M (f2torus_frac)
     const int c_first = plain ? k : 0;                      // first GLWE component with a non-zero difference
     const int j_first = c_first * level;
     const TwCtx tw = tw_setup<P>(work + (size_t)J * BUF, twT, tw_mid);
@@ -1208,8 +1225,8 @@ k_cmux(u64* __restrict__ out, const u64* __restrict__ pool, const int* __restric
 #pragma unroll
             for (int j1 = 0; j1 < R1; j1++) {
                 const int c0 = (j1 << P::LOGL1) + j2;
-                dst[c0] = src[c0] + f2torus(z[j1].x * g.inv_M);
-                dst[M + c0] = src[M + c0] + f2torus(z[j1].y * g.inv_M);
+                dst[c0] = src[c0] + f2torus_frac(z[j1].x, tscale);
+                dst[M + c0] = src[M + c0] + f2torus_frac(z[j1].y, tscale);
             }
         }
         csync<C>();
@@ -1256,6 +1273,8 @@ static int launch_clustered(Kern kern, int C, int NT, int tmem_cols, size_t smem
     FHE_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
     return 0;
 }
+
+extern int g_pbs_pipeline;    // pbs.cu: k_pbs_pipe enabled (default 1, FHE_PBS_PIPE=0 / fhe_pbs_set_pipeline)
 
 struct PbsLaunchArgs {
     // common
@@ -1315,10 +1334,12 @@ struct PbsPlanOps {
     static size_t smem_pipe() { return (size_t)2 * P::S * 8 + (size_t)5 * P::BUF * 16; }
     static int pbs(const PbsLaunchArgs& a) {
         if constexpr (P::PIPE) {
-            // development knob, read once: FHE_PBS_PIPE=0 runs the plan's generic kernel (A/B measurements)
-            static const bool use_pipe = [] { const char* e = getenv("FHE_PBS_PIPE"); return !(e && e[0] == '0'); }();
+            // fhe_pbs_set_pipeline(0) / FHE_PBS_PIPE=0 run the plan's generic kernel instead: both kernels perform the same
+            // floating-point operations in the same order, so their outputs must be BIT-IDENTICAL (the race test)
+            const bool use_pipe = g_pbs_pipeline != 0;
             const bool plain = !(a.bsk_ct_stride || a.g.nout > 1 || a.g.theta > 0);
-            if (use_pipe && plain && a.g.k == 1 && a.g.level == 2 && 2 * a.g.base_log <= 30 && a.g.base_log >= 2)
+            const bool fits = use_pipe && plain && a.g.k == 1 && a.g.level == 2 && 2 * a.g.base_log <= 30 && a.g.base_log >= 2;
+            if (fits)
                 return launch_clustered(k_pbs_pipe<P>, P::C, P::NT, P::TM_CTA, smem_pipe(), a.B, a.st, a.out, a.in, a.B,
                                         a.bskF, a.luts, a.lut_idx, a.g, a.twT, a.tw_mid, a.prof);
         }

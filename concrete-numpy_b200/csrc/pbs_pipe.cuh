@@ -37,19 +37,6 @@ __device__ __forceinline__ void mbar_arrive(u64* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// x * scale (scale = 2^-64 / M) -> torus word: the fractional part of the scaled value, read straight out of the mantissa
-// of (frac + 1.5) in [1, 2].  5 FP64 + 3 integer operations instead of the 10 + 6 of f2torus; the result is rounded to a
-// multiple of 2^12 (2^-52 of the torus), 2^28 times below the fp64 FFT's own error at these sizes.
-__device__ __forceinline__ u64 f2torus_frac(double x, double scale) {
-    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
-    const double y = x * scale;
-    const double f = y - ((y + MAGIC) - MAGIC);              // y - rint(y) in [-0.5, 0.5], exact
-    const double t = f + 1.5;
-    const unsigned hi = (unsigned)__double2hiint(t), lo = (unsigned)__double2loint(t);
-    // mantissa << 12 (sign and exponent fall off the top), minus 2^63
-    return ((u64)(((hi << 12) | (lo >> 20)) ^ 0x80000000u) << 32) | (u64)(lo << 12);
-}
-
 // A thread owns IPT = Q / NT items of every polynomial (item ii: q = tid + ii * NT); an item is the 2*R1 coefficients of one
 // stage-1 butterfly.  IPT * R1 = L1 / NT is the same for every plan with the same L1 and thread count (8 for L1 = 2048,
 // 256 threads): R1 = 8 -> one radix-8 item, R1 = 2 -> four radix-2 items, and the per-thread register / tensor-memory

@@ -137,6 +137,9 @@ int fhe_blind_rotate_batch(uint64_t* out, const uint64_t* in, long B, const void
 /* development aid: k_pbs accumulates per-phase clock64() deltas of CTA b < 16 into dev_buf[16*b .. 16*b+15]
  * (NULL switches it off); not part of the reference-facing surface */
 int fhe_pbs_set_profile(long long* dev_buf);
+/* test / measurement hook: 0 makes the pipelined bootstrap plans (k_pbs_pipe) run their generic kernel; returns the
+ * previous setting.  Both kernels are bit-identical by construction; not part of the reference-facing surface */
+int fhe_pbs_set_pipeline(int enabled);
 
 /* ---- torus linear algebra on [E][L] tensors (L = kN+1) --------------------------------
  * ia / ib: optional int32 row maps (numpy broadcasting resolved by the host), NULL = identity.

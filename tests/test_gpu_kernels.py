@@ -261,6 +261,40 @@ def test_pbs_plan_variants_agree(cuda_device, p_bits, n, k, N, level, base_log):
     assert all(c >= 1 for c in ev._capacity)
 
 
+@pytest.mark.parametrize("p_bits,N,base_log", [(8, 32768, 15), (7, 16384, 15), (6, 8192, 13)])
+def test_pipelined_bootstrap_is_bit_identical_to_the_generic_kernel(cuda_device, p_bits, N, base_log):
+    """k_pbs_pipe (pbs_pipe.cuh) replaces the cluster barriers of k_pbs by per-buffer mbarriers and split handshakes; it
+    performs the same floating-point operations in the same order, so every output WORD must equal the generic kernel's
+    (fhe_pbs_set_pipeline switches between them at run time).  A lost or early exchange -- the class of error a missing
+    handshake causes -- corrupts an accumulator and shows up here as a mismatch.  CNP_B200_STRESS=1 runs the long form
+    (the race fixed in round 2 appeared about once per 10^7 CMUX iterations)."""
+    stress = os.environ.get("CNP_B200_STRESS", "0") not in ("", "0")
+    n, B = (996, 3840) if stress else (160, 480)
+    p = E.CryptoParams(p=p_bits, n=n, k=1, N=N, pbs_level=2, pbs_base_log=base_log, ks_level=8, ks_base_log=3,
+                       lwe_std=2.0 ** -40, glwe_std=2.0 ** -55)
+    ks = E.KeySet(p, cuda_device, seed=21)
+    ev = E.EvalKeys.of(ks)
+    rng = np.random.default_rng(N)
+    m = rng.integers(0, 1 << p_bits, B).astype(np.uint64)
+    tables = rng.integers(0, 1 << p_bits, (2, 1 << p_bits))
+    lut_idx = torch.from_numpy(rng.integers(0, 2, B).astype(np.int32)).to(cuda_device)
+    luts = E.from_np_u64(E.build_lut_accumulators(p, tables), cuda_device)
+    small = E.keyswitch(ev, E.encrypt(ks, m))
+    lib = _lib.load()
+    prev = lib.fhe_pbs_set_pipeline(1)
+    try:
+        piped = [E.to_np_u64(E.bootstrap(ev, small, luts, lut_idx)) for _ in range(2)]
+        lib.fhe_pbs_set_pipeline(0)
+        generic = E.to_np_u64(E.bootstrap(ev, small, luts, lut_idx))
+    finally:
+        lib.fhe_pbs_set_pipeline(prev)
+    exp = tables[lut_idx.cpu().numpy(), m.astype(np.int64)].astype(np.uint64)
+    assert np.array_equal(E.decrypt(ks, E.from_np_u64(generic, cuda_device)), exp)
+    for out in piped:
+        bad = np.nonzero((out != generic).any(axis=1))[0]
+        assert bad.size == 0, (bad[:8].tolist(), int(bad.size))
+
+
 def test_linear_ops_bit_exact(oracle, cuda_device):
     rng = np.random.default_rng(3)
     L = 2049
