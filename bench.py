@@ -415,9 +415,11 @@ def run_ours(args):
             circ, enc_, ev_, expected = open_config(name)
             out_ = circ.server.run(enc_, ev_)                       # warm-up + correctness
             ok_ = bool(same(circ.decrypt(out_), expected))
-            with LinearTimer(E, torch) as lt:
-                circ.server.run(enc_, ev_)
-                lin = lt.summary(hbm_gbs)
+            lin = None
+            if name.startswith(("cfg3", "cfg4")):
+                with LinearTimer(E, torch) as lt:
+                    circ.server.run(enc_, ev_)
+                    lin = lt.summary(hbm_gbs)
             t_ms, _ = time_run(circ, enc_, ev_)
             p_ = circ.server.client_specs.client_parameters.crypto
             n_pbs_ = int(circ.server._feedback.n_pbs)

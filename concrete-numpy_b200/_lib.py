@@ -36,6 +36,7 @@ _SIGS = {
     "fhe_bsk_to_fourier": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_pbs_batch": (C.c_int, [_p, _p, C.c_long, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_pbs_num_variants": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "fhe_pbs_variant_pipelined": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "fhe_pbs_variant_cluster_size": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "fhe_pbs_variant_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_pbs_variant_capacity": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -47,6 +48,7 @@ _SIGS = {
     "fhe_blind_rotate_batch": (C.c_int, [_p, _p, C.c_long, _p, C.c_long, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_pbs_set_profile": (C.c_int, [_p]),
     "fhe_pbs_set_pipeline": (C.c_int, [C.c_int]),
+    "fhe_pbs_set_group": (C.c_int, [C.c_int]),
     "fhe_debug_polymul": (C.c_int, [_p, _p, _p, C.c_long, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_lin_add": (C.c_int, [_p, _p, _p, _p, _p, C.c_long, C.c_int, _p]),
     "fhe_lin_sub": (C.c_int, [_p, _p, _p, _p, _p, C.c_long, C.c_int, _p]),
@@ -117,3 +119,4 @@ def call(name, *args):
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise FheError(f"{name} failed with status {rc}: {lib.fhe_last_error().decode()}")
+

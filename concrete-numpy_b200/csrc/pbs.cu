@@ -76,7 +76,12 @@ static std::vector<int> fitting_plans(int N, int k, int level) {
             // at equal residency the tensor-memory accumulator plan wins (profiles/r02_*: no remote loads in P1)
             const bool tie = (threads == best_threads) && best >= 0;
             // ties: more registers per thread first (lower minb), then the tensor-memory accumulator plan
-            if (threads > best_threads || (tie && m.minb < plans[best].meta.minb) ||
+            // a pipelined plan that applies (checked above) beats the generic plans of its cluster size: it removes the
+            // cluster barriers, which matter most where a CTA has little work per CMUX
+            const bool pipe_wins = best >= 0 && m.acctm == 2 && plans[best].meta.acctm != 2;
+            const bool pipe_holds = best >= 0 && plans[best].meta.acctm == 2 && m.acctm != 2;
+            if (pipe_holds) continue;
+            if (pipe_wins || threads > best_threads || (tie && m.minb < plans[best].meta.minb) ||
                 (tie && m.minb == plans[best].meta.minb && m.acctm && !plans[best].meta.acctm)) {
                 best_threads = threads;
                 best = (int)i;
@@ -176,6 +181,7 @@ static int get_plan(int n, int k, int N, int level, int base_log, int variant, c
 
 static long long* g_prof_buf = nullptr;
 int g_pbs_pipeline = [] { const char* e = getenv("FHE_PBS_PIPE"); return (e && e[0] == '0') ? 0 : 1; }();
+int g_pbs_group = [] { const char* e = getenv("FHE_PBS_GROUP"); return (e && e[0] == '0') ? 0 : 1; }();
 
 // position of natural frequency t of the M-point spectrum inside one (j, o) slice [C][RF][BUF/RF] of a plan
 static long plan_position(const PbsPlanMeta& m, long t) {
@@ -214,6 +220,14 @@ int fhe_pbs_set_pipeline(int enabled) {
     return prev;
 }
 
+// test / measurement hook: 0 makes the grouped plans (k_pbs_group: several ciphertexts per CTA, GGSW staged once per SM)
+// run their generic kernel (k_pbs) instead; returns the previous setting.  Bit-identical by construction.
+int fhe_pbs_set_group(int enabled) {
+    const int prev = g_pbs_group;
+    g_pbs_group = enabled ? 1 : 0;
+    return prev;
+}
+
 // cluster size (CTAs per ciphertext) the on-chip layout uses for these parameters, <0 if unsupported
 int fhe_pbs_cluster_size(int N, int k, int level) {
     static const std::vector<PbsPlanEntry> plans = all_plans();
@@ -240,6 +254,15 @@ int fhe_pbs_variant_plan(int N, int k, int level, int variant, int* meta) {
     const int v[8] = {m.C, m.logR1, m.lra, m.lrb, m.lrf, m.NT, m.minb, m.kmax};
     for (int i = 0; i < 8; i++) meta[i] = v[i];
     return 0;
+}
+
+// 1 if two-level k = 1 bootstraps of this variant run the pipelined kernel (k_pbs_pipe: per-buffer mbarriers instead of
+// cluster barriers), 0 if not, < 0 if the variant does not exist
+int fhe_pbs_variant_pipelined(int N, int k, int level, int variant) {
+    static const std::vector<PbsPlanEntry> plans = all_plans();
+    const std::vector<int> fit = fitting_plans(N, k, level);
+    if (variant < 0 || variant >= (int)fit.size()) return -1;
+    return plans[fit[variant]].meta.acctm == 2 ? 1 : 0;
 }
 
 // how many ciphertexts variant `variant` bootstraps concurrently on the current device (one wave)

@@ -1,0 +1,277 @@
+// Grouped bootstrap for the single-CTA plans (N <= 2048, k = 1): one CTA per SM carries a GROUP of G ciphertexts and the
+// Fourier GGSW_i of every CMUX iteration is staged ONCE per SM in shared memory and consumed by all of them.
+//
+// k_pbs runs G independent CTAs per SM for these sizes and every CTA streams its own copy of GGSW_i from L2 inside the
+// fused pass (64 KiB per ciphertext and CMUX at N = 2048: a third of that pass is exposed L2 latency,
+// profiles/r01_pbs_p4_v1_hot_lines.txt).  Here
+//
+//   * the CTA has G * NT threads; ciphertext slot `grp` is run by threads [grp*NT, (grp+1)*NT) with the phases, the FFT
+//     factorisation and the Fourier key layout of k_pbs, synchronised by its own named barrier (bar.sync grp+1, NT), so
+//     the slots drift out of phase like independent CTAs do and overlap each other's FP64- and shared-memory-bound phases;
+//   * GGSW_i lives in a ring of (k+1)*J slices of BUF double2 (all of GGSW_i): every slice is ONE bulk asynchronous copy
+//     global -> shared (cp.async.bulk, completion on the slice's mbarrier).  A warp that has taken its values of a slice
+//     counts itself off on the slice's counter; the LAST warp of the last slot re-arms the barrier and issues the copy of
+//     the same slice of GGSW_{i+1} -- nobody blocks on a refill, and it has until the slowest slot's next fused pass
+//     (about one CMUX) to land;
+//   * one CTA per SM means the mid-pass twiddles can live in tensor memory (PbsPlan::TMEM_TW is off for the plans that run
+//     several CTAs per SM because a tcgen05.ld queues behind the other CTAs' outstanding global loads; there are none left).
+//
+// Same floating-point operations in the same order as k_pbs: the outputs are bit-identical (fhe_pbs_set_group switches at
+// run time, tests/test_gpu_kernels.py).  Shapes whose GGSW_i does not fit next to G ciphertexts (level >= 2 at N = 2048;
+// N = 4096: one ciphertext already takes 192 KiB) and the extended bootstraps of the wide path run k_pbs.
+//
+// Replaces memref_batched_bootstrap_lwe_u64 of the absent concrete-compiler runtime
+// (concrete/numpy/compilation/server.py:286, concrete/numpy/mlir/node_converter.py:1129-1208).
+#pragma once
+
+__device__ __forceinline__ void group_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ unsigned smem_atom_inc_acq_rel(unsigned* p) {
+    unsigned old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
+    return old;
+}
+__device__ __forceinline__ void bulk_copy_from_global(void* dst_smem, const void* src, unsigned bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <class P, int G>
+struct PbsGroup {
+    static constexpr int NTC = P::NT * G;                       // threads per CTA
+    static constexpr int TM_T = P::TM_A + P::TM_B;              // tensor-memory columns per thread (mid-pass twiddles)
+    static constexpr int TM_NEED = TM_T * ((NTC + 127) / 128);
+    static constexpr int TM_COLS = TM_NEED <= 32 ? 32 : TM_NEED <= 64 ? 64 : TM_NEED <= 128 ? 128 : TM_NEED <= 256 ? 256 : 512;
+    static constexpr int MAX_SLICES = 8;                        // (k+1) * J with k = 1, level <= 4
+    static_assert(P::C == 1 && P::KMAX == 1 && TM_NEED <= 512 && NTC <= 1024, "grouped bootstrap: single-CTA plan, k = 1");
+    static_assert(P::NT == 2 * (P::BUF / P::RF), "fused pass: thread pair (w, w + NG) shares butterfly group w");
+    static size_t smem(const PbsGeom& g) {
+        return (size_t)G * ((size_t)2 * P::S * 8 + (size_t)g.J * P::BUF * 16) + (size_t)2 * g.J * P::BUF * 16;
+    }
+};
+
+template <class P, int G>
+__global__ void __launch_bounds__(P::NT * G, 1)
+k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* __restrict__ bskF,
+            const u64* __restrict__ luts, const int* __restrict__ lut_idx, const PbsGeom g,
+            const double2* __restrict__ twT, const double2* __restrict__ tw_mid, long long* prof) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using GP = PbsGroup<P, G>;
+    constexpr int NT = P::NT, R1 = P::R1, RF = P::RF, BUF = P::BUF, S = P::S, N = P::N;
+    constexpr int NG = BUF / RF;                                  // butterfly groups of the fused pass
+    constexpr unsigned BUF_BYTES = (unsigned)(sizeof(double2) << P::LOGBUF);
+    constexpr unsigned WARPS_PER_SLICE = NG / 32;                 // warps of one ciphertext slot that read a given slice
+    const int J = g.J, level = g.level, base_log = g.base_log;
+    const int tid = (int)threadIdx.x % NT, grp = (int)threadIdx.x / NT;
+    const int bar_id = 1 + grp;
+    const int nslices = 2 * J;
+    __shared__ __align__(8) u64 s_full[GP::MAX_SLICES];           // slice s of the current GGSW has landed
+    __shared__ unsigned s_cnt[GP::MAX_SLICES];                    // warps that have taken their values of slice s
+    __shared__ unsigned s_tmem_base;
+    // shared memory: per slot [ACC 2*S u64][work J*BUF double2], then the GGSW ring [2J][BUF]
+    const size_t slot_bytes = (size_t)2 * S * 8 + (size_t)J * BUF * 16;
+    u64* acc = reinterpret_cast<u64*>(smem_raw + (size_t)grp * slot_bytes);
+    double2* work = reinterpret_cast<double2*>(acc + 2 * (size_t)S);
+    double2* ring = reinterpret_cast<double2*>(smem_raw + (size_t)G * slot_bytes);
+    const size_t ggsw_stride = (size_t)J * 2 * BUF;               // double2 per CMUX iteration
+    const double tscale = g.inv_M * 5.42101086242752217e-20;      // 2^-64 / M
+    const bool do_prof = (prof != nullptr) && blockIdx.x == 0 && threadIdx.x == 0;
+    long long t_last = do_prof ? clock64() : 0;
+#define GROUP_PROF(slot)                       \
+    if (do_prof) {                             \
+        const long long t_now = clock64();     \
+        prof[slot] += t_now - t_last;          \
+        t_last = t_now;                        \
+    }
+
+    // ciphertext of slot `grp` in round r: r * (grid * G) + grp * grid + blockIdx.x -- the first slots of all CTAs fill
+    // before the second ones, so a small batch spreads over the SMs; the CTA is active in a round iff its slot 0 is
+    const long grid = gridDim.x, per_round = grid * G;
+    const long my_rounds = (B > (long)blockIdx.x + grp * grid) ? (B - blockIdx.x - grp * grid + per_round - 1) / per_round : 0;
+    const long cta_rounds = (B > (long)blockIdx.x) ? (B - blockIdx.x + per_round - 1) / per_round : 0;
+    const long total_iters = cta_rounds * g.n;                    // GGSWs this CTA stages
+
+    // ---- set-up: tensor-memory twiddles, barriers, the first GGSW
+    {
+        const int warp = (int)threadIdx.x >> 5;
+        if (warp == 0) tmem_alloc(&s_tmem_base, GP::TM_COLS);
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < nslices; s++) {
+                mbar_init(&s_full[s], 1);
+                s_cnt[s] = 0;
+            }
+            mbar_fence_init();
+        }
+        tmem_fence_before_sync();
+        __syncthreads();
+        tmem_fence_after_sync();
+        if (threadIdx.x == 0 && total_iters > 0)
+            for (int s = 0; s < nslices; s++) {
+                mbar_arm(&s_full[s], BUF_BYTES);
+                bulk_copy_from_global(ring + ((size_t)s << P::LOGBUF), bskF + ((size_t)s << P::LOGBUF), BUF_BYTES, &s_full[s]);
+            }
+    }
+    TwCtx tw;
+    tw.twT = twT;
+    tw.sA = tw.sB = nullptr;
+    tw.base = s_tmem_base;
+    tw.tA = tw.base + ((unsigned)((((int)threadIdx.x >> 5) & 3) * 32) << 16) + (unsigned)(((int)threadIdx.x >> 7) * GP::TM_T);
+    tw.tB = tw.tA + P::TM_A;
+    tw.tAcc = 0;
+    if constexpr (P::LRA > 0) tw_init_pass<P::LRA, P::LOGL1, P::LOGBUF, NT>(tw.tA, tw_mid, tid);
+    if constexpr (P::LRB > 0) tw_init_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, NT>(tw.tB, tw_mid + P::TWA, tid);
+    tmem_wait_st();
+
+    long it = 0;                                                  // GGSWs consumed so far by this slot (== by the CTA)
+    for (long r = 0; r < my_rounds; r++) {
+        const long ct = r * per_round + grp * grid + blockIdx.x;
+        // ciphertext slots of this CTA that are active in this round (slot s is active iff its ciphertext exists)
+        unsigned active = 0;
+        for (int s = 0; s < G; s++) active += (r * per_round + s * grid + blockIdx.x < B) ? 1u : 0u;
+        const unsigned expect = active * WARPS_PER_SLICE;
+        const u64* lwe = in + (size_t)ct * (g.n + 1);
+        const u64* lut = luts + (size_t)(lut_idx ? lut_idx[ct] : 0) * 2 * N;
+        int a_next = modswitch(lwe[0], g.logN);
+        {
+            // ---- ACC = X^{-b~} * LUT
+            const int a0 = (2 * N - modswitch(lwe[g.n], g.logN)) & (2 * N - 1);
+            for (int w = tid; w < 2 * S; w += NT) {
+                const int c = w >> P::LOGS, s = w & (S - 1);
+                const int v = (slot_to_coef<P>(s, 0) - a0) & (2 * N - 1);
+                const u64 x = lut[(size_t)c * N + (v & (N - 1))];
+                acc[w] = (v >> (P::LOGM + 1)) ? (0ULL - x) : x;
+            }
+        }
+        group_sync(bar_id, NT);
+
+        for (int i = 0; i < g.n; i++, it++) {
+            const int a = a_next;
+            a_next = (i + 1 < g.n) ? modswitch(lwe[i + 1], g.logN) : 0;
+            // ---- P1: rotate, subtract, decompose, fold + twist, radix-R1 stage
+            if (level * base_log <= 30)
+                p1_items<P, unsigned>(acc, work, 0, a, g, tw, tid);
+            else
+                p1_items<P, u64>(acc, work, 0, a, g, tw, tid);
+            group_sync(bar_id, NT);
+            GROUP_PROF(0)
+            // ---- P2: forward mid passes of the J digit polynomials
+            if constexpr (P::LRA > 0) {
+                mid_pass<P::LRA, P::LOGL1, P::LOGBUF, NT, false, true, 4>(work, J, tw.tA, nullptr, 1, tid);
+                group_sync(bar_id, NT);
+            }
+            if constexpr (P::LRB > 0) {
+                mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, NT, false, true, 4>(work, J, tw.tB, nullptr, 1, tid);
+                group_sync(bar_id, NT);
+            }
+            GROUP_PROF(2)
+            // ---- P3: last forward pass + multiply-accumulate against the staged GGSW_i + first inverse pass.  Thread pair
+            // (w, w + NG) shares butterfly group w; thread (w, o) accumulates output polynomial o and reads slices 2*j + o
+            {
+                const int w = tid % NG, o = tid / NG;
+                const unsigned par = (unsigned)(it & 1);
+                const long it_next = it + 1;
+                const double2* gnext_global = bskF + (size_t)((i + 1 < g.n) ? i + 1 : 0) * ggsw_stride;
+                double2 r[RF], gv[RF];
+                mbar_wait(&s_full[o], par);
+                {
+                    const double2* gs = ring + ((size_t)o << P::LOGBUF) + w;
+#pragma unroll
+                    for (int m = 0; m < RF; m++) {
+                        r[m] = make_double2(0.0, 0.0);
+                        gv[m] = gs[m * NG];
+                    }
+                }
+#pragma unroll 1
+                for (int j = 0; j < J; j++) {
+                    double2 x[RF];
+                    const double2* base = work + ((size_t)j << P::LOGBUF);
+#pragma unroll
+                    for (int m = 0; m < RF; m++) x[m] = base[SW(w * RF + m)];
+                    Dft<RF, false>::run(x);
+                    const bool more = (j + 1 < J);
+                    const int sl = 2 * j + o;
+                    const double2* gn = ring + ((size_t)(sl + 2) << P::LOGBUF) + w;
+                    if (more) mbar_wait(&s_full[sl + 2], par);
+#pragma unroll
+                    for (int m = 0; m < RF; m++) {
+                        const double2 b = gv[m];
+                        r[m].x = fma(x[m].x, b.x, r[m].x);
+                        r[m].x = fma(-x[m].y, b.y, r[m].x);
+                        r[m].y = fma(x[m].x, b.y, r[m].y);
+                        r[m].y = fma(x[m].y, b.x, r[m].y);
+                        if (more) gv[m] = gn[m * NG];
+                    }
+                    // this warp holds its values of slice sl in registers (they were requested one step ahead): count it
+                    // off; the last warp of the last slot refills the slice with GGSW_{i+1} (next round: GGSW_0)
+                    __syncwarp();
+                    if ((tid & 31) == 0) {
+                        const unsigned old = smem_atom_inc_acq_rel(&s_cnt[sl]);
+                        if (old + 1 == expect) {
+                            s_cnt[sl] = 0;
+                            if (it_next < total_iters) {
+                                mbar_arm(&s_full[sl], BUF_BYTES);
+                                bulk_copy_from_global(ring + ((size_t)sl << P::LOGBUF), gnext_global + ((size_t)sl << P::LOGBUF),
+                                                      BUF_BYTES, &s_full[sl]);
+                            }
+                        }
+                    }
+                }
+                group_sync(bar_id, NT);      // the partner thread still reads the buffers the outputs overwrite
+                Dft<RF, true>::run(r);
+                double2* base = work + ((size_t)o << P::LOGBUF);
+#pragma unroll
+                for (int m = 0; m < RF; m++) base[SW(w * RF + m)] = r[m];
+            }
+            group_sync(bar_id, NT);
+            GROUP_PROF(3)
+            // ---- P4: inverse mid passes of the two output polynomials
+            if constexpr (P::LRB > 0) {
+                mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, NT, true, true, 4>(work, 2, tw.tB, nullptr, 1, tid);
+                group_sync(bar_id, NT);
+            }
+            if constexpr (P::LRA > 0) {
+                mid_pass<P::LRA, P::LOGL1, P::LOGBUF, NT, true, true, 4>(work, 2, tw.tA, nullptr, 1, tid);
+                group_sync(bar_id, NT);
+            }
+            GROUP_PROF(4)
+            // ---- P5: inverse radix-R1 stage, untwist, round, ACC +=
+#pragma unroll 1
+            for (int itm = tid; itm < (2 << P::LOGQ); itm += NT) {
+                const int o = itm >> P::LOGQ, q = itm & (P::Q - 1);
+                double2 T[R1];
+                load_T<P>(T, tw, q);
+                double2 z[R1];
+                stage1_gather<P>(work + ((size_t)o << P::LOGBUF), q, T, g, z);
+                u64* acco = acc + ((size_t)o << P::LOGS);
+#pragma unroll
+                for (int j1 = 0; j1 < R1; j1++) {
+                    acco[(j1 << P::LOGQ) + q] += f2torus_frac(z[j1].x, tscale);
+                    acco[((R1 + j1) << P::LOGQ) + q] += f2torus_frac(z[j1].y, tscale);
+                }
+            }
+            group_sync(bar_id, NT);
+            GROUP_PROF(6)
+        }
+        // ---- sample extract coefficient 0
+        {
+            u64* o = out + (size_t)ct * ((size_t)N + 1);
+            for (int w = tid; w < 2 * S; w += NT) {
+                const int c = w >> P::LOGS, s = w & (S - 1);
+                const int j = slot_to_coef<P>(s, 0);
+                const u64 v = acc[w];
+                if (c < 1) {
+                    if (j == 0) o[0] = v;
+                    else o[N - j] = 0ULL - v;
+                } else if (j == 0)
+                    o[N] = v;
+            }
+        }
+        group_sync(bar_id, NT);              // the next round re-initialises the accumulator
+        GROUP_PROF(8)
+    }
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (((int)threadIdx.x >> 5) == 0) tmem_dealloc(s_tmem_base, GP::TM_COLS);
+#undef GROUP_PROF
+}

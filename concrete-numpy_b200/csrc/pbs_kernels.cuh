@@ -48,8 +48,11 @@ struct PbsGeom {
 };
 
 // Compile-time FFT plan.  M = R1 * L1, L1 = RA * RB * RF (RA / RB = 1 when absent).
-template <int C_, int LOGR1_, int LRA_, int LRB_, int LRF_, int NT_, int MINB_, int KMAX_, int ACCTM_ = 0>
+template <int C_, int LOGR1_, int LRA_, int LRB_, int LRF_, int NT_, int MINB_, int KMAX_, int ACCTM_ = 0, int GROUP_ = 0>
 struct PbsPlan {
+    // GROUP_ > 1 (single-CTA plans): k = 1 bootstraps whose GGSW fits next to GROUP_ ciphertexts run k_pbs_group
+    // (pbs_group.cuh): one CTA per SM carries GROUP_ ciphertexts and stages every GGSW_i once for all of them
+    static constexpr int GROUP = GROUP_;
     static constexpr int C = C_, LOGC = (C_ == 1 ? 0 : C_ == 2 ? 1 : C_ == 4 ? 2 : C_ == 8 ? 3 : 4);
     static constexpr int LOGR1 = LOGR1_, R1 = 1 << LOGR1_;
     static constexpr int LRA = LRA_, LRB = LRB_, LRF = LRF_, RF = 1 << LRF_;
@@ -327,12 +330,13 @@ struct TwCtx {
 
 // twiddles of one mid pass for this thread's butterfly index, from the global table [(R-1)][S]
 template <int LR, int LOGLC, int LOGBUF, int NT>
-__device__ __forceinline__ void tw_init_pass(unsigned taddr, const double2* __restrict__ tw_g) {
+__device__ __forceinline__ void tw_init_pass(unsigned taddr, const double2* __restrict__ tw_g, int tix = -1) {
     constexpr int R = 1 << LR;
     constexpr int LOGSS = LOGLC - LR, SS = 1 << LOGSS;
     constexpr int NBF = 1 << (LOGBUF - LR);
     constexpr int TMW = (4 * (R - 1) <= 4) ? 4 : (4 * (R - 1) <= 16) ? 16 : (4 * (R - 1) <= 32) ? 32 : 64;
-    const int w = (NBF >= NT) ? (int)threadIdx.x : (int)(threadIdx.x % NBF);
+    const int tx = (tix < 0) ? (int)threadIdx.x : tix;
+    const int w = (NBF >= NT) ? tx : (tx % NBF);
     const int q = w & (SS - 1);
     double2 t[TMW / 4];
 #pragma unroll
@@ -382,7 +386,7 @@ __device__ __forceinline__ void tw_teardown(const TwCtx& tw) {
 // ---- one mid pass over `nbuf` buffers of BUF points, sub-transform length 2^LOGLC ------------
 // forward (DIF): y_m = DFT_R(x)_m * W_Lc^{q m};   inverse (DIT): mirror with conjugates.
 // A thread keeps the R-1 twiddles of its butterfly index in registers across the buffers it handles.
-template <int LR, int LOGLC, int LOGBUF, int NT, bool INV, bool TM>
+template <int LR, int LOGLC, int LOGBUF, int NT, bool INV, bool TM, int TMQ = 0 /* > 0: tensor-memory twiddles are fetched TMQ at a time (128-register kernels) */>
 __device__ __forceinline__ void mid_pass(double2* __restrict__ work, int nbuf, unsigned tw_taddr /* TMEM */,
                                          const double2* __restrict__ tw /* shared: [(R-1)][S] */,
                                          int bstep = 1 /* distance between the buffers, in buffers */,
@@ -417,7 +421,20 @@ __device__ __forceinline__ void mid_pass(double2* __restrict__ work, int nbuf, u
             double2 x[R];
 #pragma unroll
             for (int r = 0; r < R; r++) x[r] = base[SW(pos0 + (r << LOGSS))];
-            if (!INV) {
+            if constexpr (TM_IN_LOOP && TMQ > 0) {
+                // 128-register kernels: the twiddles arrive TMQ at a time (TMW / 4 of them next to the R data points spill)
+                static_assert((TMW / 4) % TMQ == 0, "whole chunks");
+                if (!INV) Dft<R, false>::run(x);
+#pragma unroll
+                for (int c0 = 0; c0 < TMW / 4; c0 += TMQ) {
+                    double2 tq[TMQ];
+                    tmem_load_c<TMQ>(tw_taddr + 4 * c0, tq);
+#pragma unroll
+                    for (int e = 0; e < TMQ; e++)
+                        if (c0 + e + 1 < R) x[c0 + e + 1] = INV ? cmulc(x[c0 + e + 1], tq[e]) : cmul(x[c0 + e + 1], tq[e]);
+                }
+                if (INV) Dft<R, true>::run(x);
+            } else if (!INV) {
                 Dft<R, false>::run(x);
                 // tensor-memory twiddles are re-read per buffer right where they are needed: a ~75-cycle load
                 // is cheaper than 64 registers held across the butterfly
@@ -540,7 +557,8 @@ __device__ __forceinline__ size_t ggsw_slice(int j, int o, int k, int rank) {
 // level*base_log bits fit 30 bits (halves the registers of the decomposition state).
 template <class P, typename ST>
 __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* __restrict__ work, int rank, int a,
-                                         const PbsGeom& g, const TwCtx& tw) {
+                                         const PbsGeom& g, const TwCtx& tw,
+                                         int tix = -1 /* thread index inside the NT threads of this ciphertext (default: threadIdx.x) */) {
     constexpr int C = P::C, R1 = P::R1, NT = P::NT, Q = P::Q, N = P::N;
     const int k = g.k, level = g.level, base_log = g.base_log;
     const ST mask = (ST)((1ULL << base_log) - 1);
@@ -549,7 +567,7 @@ __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* _
     // small stage-1 radices mean many light items per thread: unroll them for instruction-level parallelism
     constexpr int ITEM_UNROLL = (R1 <= 2) ? 4 : (R1 <= 4) ? 2 : 1;
 #pragma unroll ITEM_UNROLL
-    for (int it = threadIdx.x; it < ((k + 1) << P::LOGQ); it += NT) {
+    for (int it = (tix < 0 ? (int)threadIdx.x : tix); it < ((k + 1) << P::LOGQ); it += NT) {
         const long long t_a = do_prof ? clock64() : 0;
         const int c = it >> P::LOGQ, q = it & (Q - 1);
         const int j2 = (rank << P::LOGQ) + q;
@@ -1235,6 +1253,7 @@ k_cmux(u64* __restrict__ out, const u64* __restrict__ pool, const int* __restric
 }
 
 #include "pbs_pipe.cuh"
+#include "pbs_group.cuh"
 
 // ------------------------------------------------------------------ host launch helpers ----
 template <typename Kern, typename... Args>
@@ -1275,6 +1294,23 @@ static int launch_clustered(Kern kern, int C, int NT, int tmem_cols, size_t smem
 }
 
 extern int g_pbs_pipeline;    // pbs.cu: k_pbs_pipe enabled (default 1, FHE_PBS_PIPE=0 / fhe_pbs_set_pipeline)
+extern int g_pbs_group;       // pbs.cu: k_pbs_group enabled (default 1, FHE_PBS_GROUP=0 / fhe_pbs_set_group)
+
+// one CTA per SM, GROUP ciphertexts per CTA (k_pbs_group)
+template <typename Kern, typename... Args>
+static int launch_grouped(Kern kern, int threads, size_t smem, long B, cudaStream_t st, Args... args) {
+    FHE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 0;
+    FHE_CUDA(cudaGetDevice(&dev));
+    FHE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(threads);
+    cfg.gridDim = dim3((unsigned)((long)sms < B ? (long)sms : B));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    FHE_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+    return 0;
+}
 
 struct PbsLaunchArgs {
     // common
@@ -1333,6 +1369,14 @@ struct PbsPlanOps {
     }
     static size_t smem_pipe() { return (size_t)2 * P::S * 8 + (size_t)5 * P::BUF * 16; }
     static int pbs(const PbsLaunchArgs& a) {
+        if constexpr (P::GROUP > 1) {
+            // fhe_pbs_set_group(0) / FHE_PBS_GROUP=0 run the plan's generic kernel instead (bit-identical outputs)
+            using GP = PbsGroup<P, P::GROUP>;
+            const bool plain = !(a.bsk_ct_stride || a.g.nout > 1 || a.g.theta > 0);
+            if (g_pbs_group != 0 && plain && a.g.k == 1 && GP::smem(a.g) + 2048 <= PBS_SMEM_MAX)
+                return launch_grouped(k_pbs_group<P, P::GROUP>, GP::NTC, GP::smem(a.g), a.B, a.st, a.out, a.in, a.B, a.bskF,
+                                      a.luts, a.lut_idx, a.g, a.twT, a.tw_mid, a.prof);
+        }
         if constexpr (P::PIPE) {
             // fhe_pbs_set_pipeline(0) / FHE_PBS_PIPE=0 run the plan's generic kernel instead: both kernels perform the same
             // floating-point operations in the same order, so their outputs must be BIT-IDENTICAL (the race test)

@@ -128,8 +128,8 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
     constexpr int N = P::N;
     constexpr int NG = BUF / RF;
     constexpr int IPT = Q / NT;               // items per thread and polynomial
-    static_assert(P::ACC_TM && P::TMEM_TW && C >= 2 && Q % NT == 0 && NG == NT && IPT * R1 * 4 <= 64,
-                  "pipelined bootstrap: whole items per thread, one fused-pass group per thread");
+    static_assert(P::ACC_TM && P::TMEM_TW && C >= 2 && Q % NT == 0 && (NG == NT || 2 * NG == NT) && IPT * R1 * 4 <= 64,
+                  "pipelined bootstrap: whole items per thread; one fused-pass group per thread, or per thread pair (one output each)");
     static_assert(S * 8 == BUF * 16, "a rotated-accumulator half doubles as a staging buffer");
     constexpr unsigned BUF_BYTES = (unsigned)(sizeof(double2) << P::LOGBUF);
     const bool do_prof = (prof != nullptr) && blockIdx.x < 16 && threadIdx.x == 0;
@@ -164,8 +164,9 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
     unsigned ph = 0;
     const int j2_0 = (rank << P::LOGQ) + tid;         // item ii of this thread: q = tid + ii * NT, j2 = j2_0 + ii * NT
     // the stage-1 twiddles of this thread's items never change: they live in the tensor-memory columns the plan leaves free
-    static_assert(2 * P::TM_THREAD + 2 * 4 * IPT * R1 <= 512 && P::TM_CTA == 512, "room for the stage-1 twiddles");
-    const unsigned tT = tw.base + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)(2 * P::TM_THREAD + (tid >> 7) * 4 * IPT * R1);
+    constexpr int TM_SLOTS = (NT + 127) / 128;       // thread slots per tensor-memory lane
+    static_assert(TM_SLOTS * (P::TM_THREAD + 4 * IPT * R1) <= P::TM_CTA, "room for the stage-1 twiddles");
+    const unsigned tT = tw.base + ((unsigned)(((tid >> 5) & 3) * 32) << 16) + (unsigned)(TM_SLOTS * P::TM_THREAD + (tid >> 7) * 4 * IPT * R1);
     {
         double2 T[IPT * R1];
 #pragma unroll
@@ -285,20 +286,23 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 for (int b = 0; b < 4; b++) mbar_arm(&s_bar[b], BUF_BYTES);      // next CMUX
             mid_pass<P::LRA, P::LOGL1, P::LOGBUF, NT, false, true>(work + BUF, 2, tw.tA, tw.sA, 2);
             __syncthreads();
-            // the GGSW values of the first digit polynomial are requested before the last mid pass: their L2 latency
-            // hides behind it instead of opening the multiply-accumulate
-            const double2* gp = bskF + (size_t)i * ggsw_stride + ((size_t)rank << P::LOGBUF) + tid;
+            const double2* gp = bskF + (size_t)i * ggsw_stride + ((size_t)rank << P::LOGBUF);
             const size_t o_stride = (size_t)C << P::LOGBUF;
-            double2 gv[2][RF];
+            if constexpr (NG == NT) {
+                // the GGSW values of the first digit polynomial are requested before the last mid pass: their L2 latency
+                // hides behind it instead of opening the multiply-accumulate
+                gp += tid;
+                double2 gv[2][RF];
 #pragma unroll
-            for (int o = 0; o < 2; o++)
+                for (int o = 0; o < 2; o++)
 #pragma unroll
-                for (int m = 0; m < RF; m++) gv[o][m] = __ldg(gp + o * o_stride + m * NG);
-            mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, NT, false, true>(work + BUF, 2, tw.tB, tw.sB, 2);
-            __syncthreads();
-            PIPE_PROF(2)
-            // ---------------- P3: last forward pass + multiply-accumulate against GGSW_i + first inverse pass
-            {
+                    for (int m = 0; m < RF; m++) gv[o][m] = __ldg(gp + o * o_stride + m * NG);
+                if constexpr (P::LRB > 0) {
+                    mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, NT, false, true>(work + BUF, 2, tw.tB, tw.sB, 2);
+                    __syncthreads();
+                }
+                PIPE_PROF(2)
+                // ---------------- P3: last forward pass + multiply-accumulate against GGSW_i + first inverse pass
                 double2 r[2][RF];
 #pragma unroll
                 for (int o = 0; o < 2; o++)
@@ -332,6 +336,47 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
 #pragma unroll
                     for (int m = 0; m < RF; m++) base[SW(tid * RF + m)] = r[o][m];
                 }
+            } else {
+                // half as many fused-pass groups as threads (small local transforms): thread pair (w, w + NG) shares group
+                // w, each thread accumulates ONE output polynomial (o = tid / NG) -- the last forward radix pass is computed
+                // by both, the GGSW loads and multiply-adds are split
+                const int w = tid % NG, o = tid / NG;
+                gp += w + (size_t)o * o_stride;
+                double2 gv[RF];
+#pragma unroll
+                for (int m = 0; m < RF; m++) gv[m] = __ldg(gp + m * NG);
+                if constexpr (P::LRB > 0) {
+                    mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, NT, false, true>(work + BUF, 2, tw.tB, tw.sB, 2);
+                    __syncthreads();
+                }
+                PIPE_PROF(2)
+                double2 r[RF];
+#pragma unroll
+                for (int m = 0; m < RF; m++) r[m] = make_double2(0.0, 0.0);
+#pragma unroll 1
+                for (int j = 0; j < 4; j++) {
+                    double2 x[RF];
+                    const double2* base = work + ((size_t)(((j & 1) << 1) | (j >> 1)) << P::LOGBUF);
+#pragma unroll
+                    for (int m = 0; m < RF; m++) x[m] = base[SW(w * RF + m)];
+                    Dft<RF, false>::run(x);
+                    const double2* gn = gp + (size_t)(j + 1) * 2 * o_stride;
+                    const bool more = (j + 1 < 4);
+#pragma unroll
+                    for (int m = 0; m < RF; m++) {
+                        const double2 b = gv[m];
+                        r[m].x = fma(x[m].x, b.x, r[m].x);
+                        r[m].x = fma(-x[m].y, b.y, r[m].x);
+                        r[m].y = fma(x[m].x, b.y, r[m].y);
+                        r[m].y = fma(x[m].y, b.x, r[m].y);
+                        if (more) gv[m] = __ldg(gn + m * NG);
+                    }
+                }
+                Dft<RF, true>::run(r);
+                __syncthreads();              // the partner thread still reads the buffers the outputs overwrite
+                double2* base = work + ((size_t)o << P::LOGBUF);
+#pragma unroll
+                for (int m = 0; m < RF; m++) base[SW(w * RF + m)] = r[m];
             }
             __syncthreads();
             cluster_arrive();                 // "my buffers 2 and 3 are free": completes behind the inverse passes

@@ -210,18 +210,28 @@ class EvalKeys:
         return self._ksk_tc
 
     def variant_for_batch(self, count: int) -> int:
-        """Largest-cluster variant that still bootstraps `count` ciphertexts in a single wave."""
+        """Plan variant for a batch of `count` ciphertexts: the largest cluster that still bootstraps them in a single
+        wave -- except that a PIPELINED variant (k_pbs_pipe: no cluster barriers) that holds the batch and is at most half
+        that cluster is faster (measured, scripts/variant_latency.py: N = 4096, 17 ciphertexts: 4.76 ms on 4 pipelined
+        CTAs vs 5.25 ms on 8; N = 8192: the pipelined plan has 2 CTAs and loses to 8)."""
         if self._capacity is None:
             lib = _lib.load()
             p = self.params
             with torch.cuda.device(self.bsk_f.device):
                 self._capacity = [lib.fhe_pbs_variant_capacity(p.N, p.k, p.pbs_level, v)
                                   for v in range(len(self.variant_clusters))]
+            self._pipelined = [p.k == 1 and p.pbs_level == 2 and 2 * p.pbs_base_log <= 30 and
+                               lib.fhe_pbs_variant_pipelined(p.N, p.k, p.pbs_level, v) == 1
+                               for v in range(len(self.variant_clusters))]
         best = 0
         for v, cap in enumerate(self._capacity):
             # 16-CTA clusters are a capacity fallback (N = 32768 with >= 3 levels), not a latency win
             if v > 0 and 0 < count <= cap and self.variant_clusters[v] <= 8:
                 best = v
+        for v, cap in enumerate(self._capacity):
+            if (v > 0 and v != best and self._pipelined[v] and 0 < count <= cap
+                    and 2 * self.variant_clusters[v] >= self.variant_clusters[best] > self.variant_clusters[v]):
+                return v
         return best
 
     def bsk_for_variant(self, v: int) -> torch.Tensor:

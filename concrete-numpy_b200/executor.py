@@ -211,6 +211,7 @@ class Executor:
         self._comm = {"allgather_calls": 0, "allgather_bytes": 0, "allreduce_calls": 0, "allreduce_bytes": 0}
         self._plans: Dict[int, dict] = {}          # per-op cached host plans + device uploads
         self._consts: Dict[str, np.ndarray] = {}
+        self._no_clear_args = all(t.encrypted for _, t in program.args)
         for op in program.ops:
             if op.name == "arith.constant":
                 self._consts[op.result] = np.asarray(op.attrs["value"], dtype=np.int64).reshape(op.result_type.dims)
@@ -306,6 +307,12 @@ class Executor:
             return None
         a = np.array(arr if dtype is None else arr.astype(dtype), copy=True, order="C")
         return torch.from_numpy(a).to(self.device)
+
+    def _static_clear(self, names) -> bool:
+        """Are these clear operands the same in every run?  Compile-time constants are; and when the function has no
+        clear argument at all, every clear value is derived from constants only.  (A table, weight or index that comes
+        from a clear ARGUMENT must be rebuilt per call.)"""
+        return self._no_clear_args or all(n in self._consts for n in names)
 
     def _plan(self, op: Op, build: Callable[[], dict]) -> dict:
         key = (id(op), self._res)
@@ -421,7 +428,7 @@ class Executor:
             cc = -cc if negate else cc
             return self._dev(self._encode(cc) if encode else np.ascontiguousarray(cc))
 
-        if cname not in self._consts:
+        if not self._static_clear([cname]):
             return build()
         key = ("clear", id(op), self._res)
         if key not in self._plans:
@@ -485,7 +492,7 @@ class Executor:
 
         # a table or map that arrives as a clear function argument can change between runs: cache constants only
         clear_names = [n for n, t in zip(op.operands, op.operand_types) if not t.encrypted]
-        plan = self._plan(op, build) if all(n in self._consts for n in clear_names) else build()
+        plan = self._plan(op, build) if self._static_clear(clear_names) else build()
         shape = op.result_type.dims
         n = _numel(shape)
         if not self._shardable(n):
@@ -523,7 +530,7 @@ class Executor:
             return {"pool": wide.lut_pool(p, luts, self.device), "polys": max(luts.shape[2] // p.N, 1), "idx": idx}
 
         clear_names = [n for n, t in zip(op.operands, op.operand_types) if not t.encrypted]
-        plan = self._plan(op, build) if all(n in self._consts for n in clear_names) else build()
+        plan = self._plan(op, build) if self._static_clear(clear_names) else build()
         rows = [self._full(x) for x in xs]
         n = rows[0].shape[0]
         if self.world == 1:
@@ -589,7 +596,7 @@ class Executor:
             return d
 
         clear_names = [n for n, t in zip(op.operands, op.operand_types) if not t.encrypted]
-        if all(n in self._consts for n in clear_names):
+        if self._static_clear(clear_names):
             plan = self._plan(op, mk)
         else:
             plan = mk()
@@ -634,7 +641,7 @@ class Executor:
             local_ok = (x.sharded and self._shardable(Mr * Nc) and Mr % self.world == 0
                         and (rows_per * K) % 2 == 0 and (rows_per * Nc) % 2 == 0)
             wname = op.operands[1]
-            if wname in self._consts:
+            if self._static_clear([wname]):
                 Wd = self._plan(op, lambda: {"W": self._dev(self._weights(W))})["W"]
             else:
                 Wd = self._dev(self._weights(W))
@@ -730,7 +737,7 @@ class Executor:
 
         # index operands that arrive as clear function arguments can change between runs: cache constants only
         clear_names = [n for n, t in zip(op.operands, op.operand_types) if not t.encrypted]
-        plan = self._plan(op, mk) if all(n in self._consts for n in clear_names) else mk()
+        plan = self._plan(op, mk) if self._static_clear(clear_names) else mk()
         if plan["identity"]:                    # a pure re-interpretation of the same rows keeps its placement
             return self._reshaped(srcs[0], shape)
         data = self._full(srcs[0]) if len(srcs) == 1 else torch.cat([self._full(s) for s in srcs], dim=0)

@@ -95,6 +95,8 @@ int fhe_pbs_batch(uint64_t* out /* [B][kN+1] */, const uint64_t* in /* [B][n+1] 
  * are meant for small batches (sequential circuits).  The Fourier BSK layout depends on the variant:
  * fhe_bsk_relayout permutes a key from one variant's layout into another's (same spectrum values). */
 int fhe_pbs_num_variants(int N, int k, int level);
+/* 1 if two-level k = 1 bootstraps of the variant run the pipelined kernel, 0 if not, < 0 if there is no such variant */
+int fhe_pbs_variant_pipelined(int N, int k, int level, int variant);
 int fhe_pbs_variant_cluster_size(int N, int k, int level, int variant);
 /* plan of a variant: meta[0..7] = cluster size, log2 of the stage-1 / mid-pass A / mid-pass B / fused radices,
  * threads per CTA, minimum CTAs per SM, largest GLWE dimension (documentation / tests) */
@@ -140,6 +142,8 @@ int fhe_pbs_set_profile(long long* dev_buf);
 /* test / measurement hook: 0 makes the pipelined bootstrap plans (k_pbs_pipe) run their generic kernel; returns the
  * previous setting.  Both kernels are bit-identical by construction; not part of the reference-facing surface */
 int fhe_pbs_set_pipeline(int enabled);
+/* the same switch for the grouped plans (k_pbs_group: several ciphertexts per CTA, each GGSW staged once per SM) */
+int fhe_pbs_set_group(int enabled);
 
 /* ---- torus linear algebra on [E][L] tensors (L = kN+1) --------------------------------
  * ia / ib: optional int32 row maps (numpy broadcasting resolved by the host), NULL = identity.

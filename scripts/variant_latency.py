@@ -7,8 +7,13 @@ from concrete_numpy_b200.params import REFERENCE_SETS
 dev = torch.device("cuda:0")
 sets = {"p5": E.CryptoParams(p=5, n=786, k=1, N=4096, pbs_level=2, pbs_base_log=13, ks_level=5, ks_base_log=3,
                              lwe_std=2.0 ** -20, glwe_std=2.0 ** -50),
-        "p4": REFERENCE_SETS[4], "p6": REFERENCE_SETS[6]}
+        "p4": REFERENCE_SETS[4], "p6": REFERENCE_SETS[6],
+        "p7": E.CryptoParams(p=7, n=920, k=1, N=16384, pbs_level=2, pbs_base_log=15, ks_level=6, ks_base_log=3,
+                             lwe_std=2.0 ** -22, glwe_std=2.0 ** -62)}
+only = sys.argv[1:]
 for name, p in sets.items():
+    if only and name not in only:
+        continue
     ks = E.KeySet(p, dev, seed=1)
     ev = E.EvalKeys.of(ks)
     table = np.arange(1 << p.p)[None, :]

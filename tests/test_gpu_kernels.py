@@ -4,6 +4,7 @@ Integer / byte work (keygen, encryption, keyswitch, linear ops) must be BIT-EXAC
 The programmable bootstrap runs an fp64 FFT: its outputs must decrypt to the exact table value and
 stay within a stated torus distance of the oracle's output on the same inputs (tolerance below).
 """
+import ctypes as C
 import os
 
 import numpy as np
@@ -257,12 +258,20 @@ def test_pbs_plan_variants_agree(cuda_device, p_bits, n, k, N, level, base_log):
     assert max(stds) <= (2.0 ** 0.5) * model_std + 2.0 ** 20, (stds, model_std)
     assert max(stds) <= 4.0 * min(stds) + 2.0 ** 20, stds
     best = max(v for v, c in enumerate(ev.variant_clusters) if v == 0 or c <= 8)
-    assert ev.variant_for_batch(1) == best and ev.variant_for_batch(100000) == 0
+    # a pipelined variant with at least half the CTAs of the largest cluster is the latency plan (N = 4096: 4 vs 8)
+    lib = _lib.load()
+    piped = [v for v, c in enumerate(ev.variant_clusters)
+             if v > 0 and level == 2 and lib.fhe_pbs_variant_pipelined(N, k, level, v) == 1
+             and 2 * c >= ev.variant_clusters[best] > c]
+    assert ev.variant_for_batch(1) == (piped[0] if piped else best) and ev.variant_for_batch(100000) == 0
+    if N == 4096:
+        assert piped and ev.variant_clusters[piped[0]] == 4
     assert all(c >= 1 for c in ev._capacity)
 
 
-@pytest.mark.parametrize("p_bits,N,base_log", [(8, 32768, 15), (7, 16384, 15), (6, 8192, 13)])
-def test_pipelined_bootstrap_is_bit_identical_to_the_generic_kernel(cuda_device, p_bits, N, base_log):
+@pytest.mark.parametrize("p_bits,N,base_log,cluster", [(8, 32768, 15, 8), (7, 16384, 15, 4), (6, 8192, 13, 2),
+                                                       (5, 4096, 13, 4)])     # the last one is a latency variant
+def test_pipelined_bootstrap_is_bit_identical_to_the_generic_kernel(cuda_device, p_bits, N, base_log, cluster):
     """k_pbs_pipe (pbs_pipe.cuh) replaces the cluster barriers of k_pbs by per-buffer mbarriers and split handshakes; it
     performs the same floating-point operations in the same order, so every output WORD must equal the generic kernel's
     (fhe_pbs_set_pipeline switches between them at run time).  A lost or early exchange -- the class of error a missing
@@ -281,16 +290,52 @@ def test_pipelined_bootstrap_is_bit_identical_to_the_generic_kernel(cuda_device,
     luts = E.from_np_u64(E.build_lut_accumulators(p, tables), cuda_device)
     small = E.keyswitch(ev, E.encrypt(ks, m))
     lib = _lib.load()
+    v = ev.variant_clusters.index(cluster)
+    meta = (C.c_int * 8)()
+    assert lib.fhe_pbs_variant_plan(N, 1, 2, v, meta) == 0 and meta[6] == 1      # the pipelined plans run one CTA per SM
     prev = lib.fhe_pbs_set_pipeline(1)
     try:
-        piped = [E.to_np_u64(E.bootstrap(ev, small, luts, lut_idx)) for _ in range(2)]
+        piped = [E.to_np_u64(E.bootstrap(ev, small, luts, lut_idx, variant=v)) for _ in range(2)]
         lib.fhe_pbs_set_pipeline(0)
-        generic = E.to_np_u64(E.bootstrap(ev, small, luts, lut_idx))
+        generic = E.to_np_u64(E.bootstrap(ev, small, luts, lut_idx, variant=v))
     finally:
         lib.fhe_pbs_set_pipeline(prev)
     exp = tables[lut_idx.cpu().numpy(), m.astype(np.int64)].astype(np.uint64)
     assert np.array_equal(E.decrypt(ks, E.from_np_u64(generic, cuda_device)), exp)
     for out in piped:
+        bad = np.nonzero((out != generic).any(axis=1))[0]
+        assert bad.size == 0, (bad[:8].tolist(), int(bad.size))
+
+
+@pytest.mark.parametrize("B", [1, 100, 148, 149, 296, 300, 1000])
+def test_grouped_bootstrap_is_bit_identical_to_the_generic_kernel(cuda_device, B):
+    """k_pbs_group (pbs_group.cuh: one CTA per SM carries two N = 2048 ciphertexts, every GGSW_i is staged once per SM by a
+    bulk copy and shared by both) performs the floating-point operations of k_pbs in the same order: every output WORD must
+    be equal (fhe_pbs_set_group switches at run time).  The batch sizes cover one slot per CTA, ragged second slots, and
+    several rounds with a ragged last one (the ring of staged GGSWs runs on across rounds)."""
+    stress = os.environ.get("CNP_B200_STRESS", "0") not in ("", "0")
+    n = 742 if stress else 96
+    p = E.CryptoParams(p=4, n=n, k=1, N=2048, pbs_level=1, pbs_base_log=23, ks_level=5, ks_base_log=3,
+                       lwe_std=2.0 ** -40, glwe_std=2.0 ** -52)
+    ks = E.KeySet(p, cuda_device, seed=22)
+    ev = E.EvalKeys.of(ks)
+    rng = np.random.default_rng(B)
+    m = rng.integers(0, 16, B).astype(np.uint64)
+    tables = rng.integers(0, 16, (2, 16))
+    lut_idx = torch.from_numpy(rng.integers(0, 2, B).astype(np.int32)).to(cuda_device)
+    luts = E.from_np_u64(E.build_lut_accumulators(p, tables), cuda_device)
+    small = E.keyswitch(ev, E.encrypt(ks, m))
+    lib = _lib.load()
+    prev = lib.fhe_pbs_set_group(1)
+    try:
+        grouped = [E.to_np_u64(E.bootstrap(ev, small, luts, lut_idx)) for _ in range(2)]
+        lib.fhe_pbs_set_group(0)
+        generic = E.to_np_u64(E.bootstrap(ev, small, luts, lut_idx))
+    finally:
+        lib.fhe_pbs_set_group(prev)
+    exp = tables[lut_idx.cpu().numpy(), m.astype(np.int64)].astype(np.uint64)
+    assert np.array_equal(E.decrypt(ks, E.from_np_u64(generic, cuda_device)), exp)
+    for out in grouped:
         bad = np.nonzero((out != generic).any(axis=1))[0]
         assert bad.size == 0, (bad[:8].tolist(), int(bad.size))
 
