@@ -181,7 +181,7 @@ static int get_plan(int n, int k, int N, int level, int base_log, int variant, c
 
 static long long* g_prof_buf = nullptr;
 int g_pbs_pipeline = [] { const char* e = getenv("FHE_PBS_PIPE"); return (e && e[0] == '0') ? 0 : 1; }();
-int g_pbs_group = [] { const char* e = getenv("FHE_PBS_GROUP"); return (e && e[0] == '0') ? 0 : 1; }();
+int g_pbs_group = [] { const char* e = getenv("FHE_PBS_GROUP"); return e ? atoi(e) : 1; }();
 
 // position of natural frequency t of the M-point spectrum inside one (j, o) slice [C][RF][BUF/RF] of a plan
 static long plan_position(const PbsPlanMeta& m, long t) {
@@ -224,7 +224,7 @@ int fhe_pbs_set_pipeline(int enabled) {
 // run their generic kernel (k_pbs) instead; returns the previous setting.  Bit-identical by construction.
 int fhe_pbs_set_group(int enabled) {
     const int prev = g_pbs_group;
-    g_pbs_group = enabled ? 1 : 0;
+    g_pbs_group = enabled;        // 0: k_pbs, 1: grouped, GGSW from L2 (default), 2: grouped, GGSW staged once per SM
     return prev;
 }
 

@@ -1,24 +1,27 @@
-// Grouped bootstrap for the single-CTA plans (N <= 2048, k = 1): one CTA per SM carries a GROUP of G ciphertexts and the
-// Fourier GGSW_i of every CMUX iteration is staged ONCE per SM in shared memory and consumed by all of them.
+// Grouped bootstrap for the single-CTA plans (N = 2048, k = 1): one CTA per SM carries a GROUP of G ciphertexts ("slots").
 //
-// k_pbs runs G independent CTAs per SM for these sizes and every CTA streams its own copy of GGSW_i from L2 inside the
-// fused pass (64 KiB per ciphertext and CMUX at N = 2048: a third of that pass is exposed L2 latency,
-// profiles/r01_pbs_p4_v1_hot_lines.txt).  Here
+// k_pbs runs G independent CTAs per SM for these sizes, which keeps its twiddle tables in shared memory (tensor memory is
+// allocated per CTA) and lets every CTA stream its own copy of GGSW_i from L2.  Here
 //
-//   * the CTA has G * NT threads; ciphertext slot `grp` is run by threads [grp*NT, (grp+1)*NT) with the phases, the FFT
-//     factorisation and the Fourier key layout of k_pbs, synchronised by its own named barrier (bar.sync grp+1, NT), so
-//     the slots drift out of phase like independent CTAs do and overlap each other's FP64- and shared-memory-bound phases;
-//   * GGSW_i lives in a ring of (k+1)*J slices of BUF double2 (all of GGSW_i): every slice is ONE bulk asynchronous copy
-//     global -> shared (cp.async.bulk, completion on the slice's mbarrier).  A warp that has taken its values of a slice
-//     counts itself off on the slice's counter; the LAST warp of the last slot re-arms the barrier and issues the copy of
-//     the same slice of GGSW_{i+1} -- nobody blocks on a refill, and it has until the slowest slot's next fused pass
-//     (about one CMUX) to land;
-//   * one CTA per SM means the mid-pass twiddles can live in tensor memory (PbsPlan::TMEM_TW is off for the plans that run
-//     several CTAs per SM because a tcgen05.ld queues behind the other CTAs' outstanding global loads; there are none left).
+//   * the CTA has G * NT threads; slot `grp` is run by threads [grp*NT, (grp+1)*NT) with the phases, the FFT factorisation
+//     and the Fourier key layout of k_pbs, synchronised by its own named barrier (bar.sync grp+1, NT), so the slots drift
+//     out of phase like independent CTAs do and overlap each other's FP64- and shared-memory-bound phases;
+//   * one CTA per SM owns all of tensor memory: the mid-pass twiddles and the stage-1 twiddles of a thread's item live in
+//     its tensor-memory lane (fetched 4 at a time: the kernel runs at 128 registers), which takes a fifth of the traffic
+//     off the shared-memory pipe -- the co-bottleneck of these shapes (ncu: shared-memory wavefronts 62 %, issue slots 62 %,
+//     FP64 pipe 46 % of peak);
+//   * RING = true (the north star's "each GGSW row staged once ... reused across the batch"): GGSW_i lives in a ring of
+//     (k+1)*J slices of BUF double2, every slice ONE bulk asynchronous copy global -> shared (cp.async.bulk, completion on
+//     the slice's mbarrier).  A warp that has taken its values of a slice counts itself off on the slice's counter; the
+//     LAST warp of the last slot re-arms the barrier and issues the copy of the same slice of GGSW_{i+1} -- nobody blocks on
+//     a refill.  MEASURED SLOWER than streaming (N = 2048, one level: 59.7 k vs 62.0 k PBS/s, k_pbs 48.5 k;
+//     profiles/r02_group_ablation.log): the staged values are read through the shared-memory pipe, which is the scarce
+//     resource here, while L2 -> SM bandwidth is not (47 MiB key, L2-resident, 8 B/clk/SM).  So RING = false is the
+//     default (fhe_pbs_set_group(2) / FHE_PBS_GROUP=2 select the ring); it also serves the shapes whose GGSW_i does not
+//     fit next to two ciphertexts (two levels) and the extended bootstraps of the wide-integer path (EXT).
 //
 // Same floating-point operations in the same order as k_pbs: the outputs are bit-identical (fhe_pbs_set_group switches at
-// run time, tests/test_gpu_kernels.py).  Shapes whose GGSW_i does not fit next to G ciphertexts (level >= 2 at N = 2048;
-// N = 4096: one ciphertext already takes 192 KiB) and the extended bootstraps of the wide path run k_pbs.
+// run time, tests/test_gpu_kernels.py).  N = 4096 cannot be grouped: one ciphertext already takes 192 KiB.
 //
 // Replaces memref_batched_bootstrap_lwe_u64 of the absent concrete-compiler runtime
 // (concrete/numpy/compilation/server.py:286, concrete/numpy/mlir/node_converter.py:1129-1208).
@@ -40,22 +43,29 @@ __device__ __forceinline__ void bulk_copy_from_global(void* dst_smem, const void
 template <class P, int G>
 struct PbsGroup {
     static constexpr int NTC = P::NT * G;                       // threads per CTA
-    static constexpr int TM_T = P::TM_A + P::TM_B;              // tensor-memory columns per thread (mid-pass twiddles)
+    // tensor-memory columns per thread: mid-pass twiddles + the R1 stage-1 twiddles of the thread's one item
+    static constexpr int TM_T = P::TM_A + P::TM_B + 4 * P::R1;
     static constexpr int TM_NEED = TM_T * ((NTC + 127) / 128);
     static constexpr int TM_COLS = TM_NEED <= 32 ? 32 : TM_NEED <= 64 ? 64 : TM_NEED <= 128 ? 128 : TM_NEED <= 256 ? 256 : 512;
     static constexpr int MAX_SLICES = 8;                        // (k+1) * J with k = 1, level <= 4
     static_assert(P::C == 1 && P::KMAX == 1 && TM_NEED <= 512 && NTC <= 1024, "grouped bootstrap: single-CTA plan, k = 1");
     static_assert(P::NT == 2 * (P::BUF / P::RF), "fused pass: thread pair (w, w + NG) shares butterfly group w");
-    static size_t smem(const PbsGeom& g) {
-        return (size_t)G * ((size_t)2 * P::S * 8 + (size_t)g.J * P::BUF * 16) + (size_t)2 * g.J * P::BUF * 16;
+    static_assert((2 << P::LOGQ) == P::NT, "one stage-1 item per thread (its twiddles are per-thread constants)");
+    static size_t smem(const PbsGeom& g, bool ring) {
+        return (size_t)G * ((size_t)2 * P::S * 8 + (size_t)g.J * P::BUF * 16) + (ring ? (size_t)2 * g.J * P::BUF * 16 : 0);
     }
 };
 
-template <class P, int G>
+// RING = false: no staging (shapes whose GGSW_i does not fit next to G ciphertexts): every slot streams GGSW_i from L2 as
+// k_pbs does; what is left of the design is one CTA per SM with G independent slots and the twiddles in tensor memory
+// EXT (never staged): the extended bootstraps of the wide-integer lookup as in k_pbs<P, true> -- one GGSW list per ciphertext
+// (bsk_ct_stride > 0) and / or a multi-output bootstrap (g.theta, g.nout)
+template <class P, int G, bool RING, bool EXT>
 __global__ void __launch_bounds__(P::NT * G, 1)
-k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* __restrict__ bskF,
+k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* __restrict__ bskF_all,
             const u64* __restrict__ luts, const int* __restrict__ lut_idx, const PbsGeom g,
-            const double2* __restrict__ twT, const double2* __restrict__ tw_mid, long long* prof) {
+            const double2* __restrict__ twT, const double2* __restrict__ tw_mid, long long* prof, size_t bsk_ct_stride) {
+    static_assert(!(RING && EXT), "extended bootstraps stream their GGSWs");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using GP = PbsGroup<P, G>;
     constexpr int NT = P::NT, R1 = P::R1, RF = P::RF, BUF = P::BUF, S = P::S, N = P::N;
@@ -106,10 +116,10 @@ k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const dou
         tmem_fence_before_sync();
         __syncthreads();
         tmem_fence_after_sync();
-        if (threadIdx.x == 0 && total_iters > 0)
+        if (RING && threadIdx.x == 0 && total_iters > 0)
             for (int s = 0; s < nslices; s++) {
                 mbar_arm(&s_full[s], BUF_BYTES);
-                bulk_copy_from_global(ring + ((size_t)s << P::LOGBUF), bskF + ((size_t)s << P::LOGBUF), BUF_BYTES, &s_full[s]);
+                bulk_copy_from_global(ring + ((size_t)s << P::LOGBUF), bskF_all + ((size_t)s << P::LOGBUF), BUF_BYTES, &s_full[s]);
             }
     }
     TwCtx tw;
@@ -119,6 +129,12 @@ k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const dou
     tw.tA = tw.base + ((unsigned)((((int)threadIdx.x >> 5) & 3) * 32) << 16) + (unsigned)(((int)threadIdx.x >> 7) * GP::TM_T);
     tw.tB = tw.tA + P::TM_A;
     tw.tAcc = 0;
+    tw.tT = tw.tB + P::TM_B;
+    {
+        double2 T[R1];
+        load_T<P>(T, tw, tid & (P::Q - 1));
+        tmem_store_c<R1>(tw.tT, T);
+    }
     if constexpr (P::LRA > 0) tw_init_pass<P::LRA, P::LOGL1, P::LOGBUF, NT>(tw.tA, tw_mid, tid);
     if constexpr (P::LRB > 0) tw_init_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, NT>(tw.tB, tw_mid + P::TWA, tid);
     tmem_wait_st();
@@ -130,12 +146,13 @@ k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const dou
         unsigned active = 0;
         for (int s = 0; s < G; s++) active += (r * per_round + s * grid + blockIdx.x < B) ? 1u : 0u;
         const unsigned expect = active * WARPS_PER_SLICE;
+        const double2* bskF = EXT ? bskF_all + (size_t)ct * bsk_ct_stride : bskF_all;
         const u64* lwe = in + (size_t)ct * (g.n + 1);
         const u64* lut = luts + (size_t)(lut_idx ? lut_idx[ct] : 0) * 2 * N;
-        int a_next = modswitch(lwe[0], g.logN);
+        int a_next = EXT ? modswitch_coarse(lwe[0], g.logN, g.theta) : modswitch(lwe[0], g.logN);
         {
             // ---- ACC = X^{-b~} * LUT
-            const int a0 = (2 * N - modswitch(lwe[g.n], g.logN)) & (2 * N - 1);
+            const int a0 = (2 * N - (EXT ? modswitch_coarse(lwe[g.n], g.logN, g.theta) : modswitch(lwe[g.n], g.logN))) & (2 * N - 1);
             for (int w = tid; w < 2 * S; w += NT) {
                 const int c = w >> P::LOGS, s = w & (S - 1);
                 const int v = (slot_to_coef<P>(s, 0) - a0) & (2 * N - 1);
@@ -147,12 +164,14 @@ k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const dou
 
         for (int i = 0; i < g.n; i++, it++) {
             const int a = a_next;
-            a_next = (i + 1 < g.n) ? modswitch(lwe[i + 1], g.logN) : 0;
+            a_next = (i + 1 < g.n) ? (EXT ? modswitch_coarse(lwe[i + 1], g.logN, g.theta) : modswitch(lwe[i + 1], g.logN)) : 0;
+            if (!RING && i + 1 < g.n && tid < nslices)      // GGSW_{i+1} -> L2 one iteration ahead
+                prefetch_l2_bulk(bskF + (size_t)(i + 1) * ggsw_stride + ((size_t)tid << P::LOGBUF), BUF_BYTES);
             // ---- P1: rotate, subtract, decompose, fold + twist, radix-R1 stage
             if (level * base_log <= 30)
-                p1_items<P, unsigned>(acc, work, 0, a, g, tw, tid);
+                p1_items<P, unsigned, true>(acc, work, 0, a, g, tw, tid);
             else
-                p1_items<P, u64>(acc, work, 0, a, g, tw, tid);
+                p1_items<P, u64, true>(acc, work, 0, a, g, tw, tid);
             group_sync(bar_id, NT);
             GROUP_PROF(0)
             // ---- P2: forward mid passes of the J digit polynomials
@@ -171,15 +190,17 @@ k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const dou
                 const int w = tid % NG, o = tid / NG;
                 const unsigned par = (unsigned)(it & 1);
                 const long it_next = it + 1;
-                const double2* gnext_global = bskF + (size_t)((i + 1 < g.n) ? i + 1 : 0) * ggsw_stride;
+                const double2* gnext_global = bskF_all + (size_t)((i + 1 < g.n) ? i + 1 : 0) * ggsw_stride;
                 double2 r[RF], gv[RF];
-                mbar_wait(&s_full[o], par);
+                // slice sl of GGSW_i as this thread reads it: the staged copy, or the key itself (L2)
+                const double2* gsl = (RING ? ring : bskF + (size_t)i * ggsw_stride) + w;
+                if (RING) mbar_wait(&s_full[o], par);
                 {
-                    const double2* gs = ring + ((size_t)o << P::LOGBUF) + w;
+                    const double2* gs = gsl + ((size_t)o << P::LOGBUF);
 #pragma unroll
                     for (int m = 0; m < RF; m++) {
                         r[m] = make_double2(0.0, 0.0);
-                        gv[m] = gs[m * NG];
+                        gv[m] = RING ? gs[m * NG] : __ldg(gs + m * NG);
                     }
                 }
 #pragma unroll 1
@@ -191,8 +212,8 @@ k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const dou
                     Dft<RF, false>::run(x);
                     const bool more = (j + 1 < J);
                     const int sl = 2 * j + o;
-                    const double2* gn = ring + ((size_t)(sl + 2) << P::LOGBUF) + w;
-                    if (more) mbar_wait(&s_full[sl + 2], par);
+                    const double2* gn = gsl + ((size_t)(sl + 2) << P::LOGBUF);
+                    if (RING && more) mbar_wait(&s_full[sl + 2], par);
 #pragma unroll
                     for (int m = 0; m < RF; m++) {
                         const double2 b = gv[m];
@@ -200,19 +221,21 @@ k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const dou
                         r[m].x = fma(-x[m].y, b.y, r[m].x);
                         r[m].y = fma(x[m].x, b.y, r[m].y);
                         r[m].y = fma(x[m].y, b.x, r[m].y);
-                        if (more) gv[m] = gn[m * NG];
+                        if (more) gv[m] = RING ? gn[m * NG] : __ldg(gn + m * NG);
                     }
-                    // this warp holds its values of slice sl in registers (they were requested one step ahead): count it
-                    // off; the last warp of the last slot refills the slice with GGSW_{i+1} (next round: GGSW_0)
-                    __syncwarp();
-                    if ((tid & 31) == 0) {
-                        const unsigned old = smem_atom_inc_acq_rel(&s_cnt[sl]);
-                        if (old + 1 == expect) {
-                            s_cnt[sl] = 0;
-                            if (it_next < total_iters) {
-                                mbar_arm(&s_full[sl], BUF_BYTES);
-                                bulk_copy_from_global(ring + ((size_t)sl << P::LOGBUF), gnext_global + ((size_t)sl << P::LOGBUF),
-                                                      BUF_BYTES, &s_full[sl]);
+                    if constexpr (RING) {
+                        // this warp holds its values of slice sl in registers (they were requested one step ahead): count
+                        // it off; the last warp of the last slot refills the slice with GGSW_{i+1} (next round: GGSW_0)
+                        __syncwarp();
+                        if ((tid & 31) == 0) {
+                            const unsigned old = smem_atom_inc_acq_rel(&s_cnt[sl]);
+                            if (old + 1 == expect) {
+                                s_cnt[sl] = 0;
+                                if (it_next < total_iters) {
+                                    mbar_arm(&s_full[sl], BUF_BYTES);
+                                    bulk_copy_from_global(ring + ((size_t)sl << P::LOGBUF), gnext_global + ((size_t)sl << P::LOGBUF),
+                                                          BUF_BYTES, &s_full[sl]);
+                                }
                             }
                         }
                     }
@@ -240,7 +263,7 @@ k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const dou
             for (int itm = tid; itm < (2 << P::LOGQ); itm += NT) {
                 const int o = itm >> P::LOGQ, q = itm & (P::Q - 1);
                 double2 T[R1];
-                load_T<P>(T, tw, q);
+                load_T<P, true>(T, tw, q);
                 double2 z[R1];
                 stage1_gather<P>(work + ((size_t)o << P::LOGBUF), q, T, g, z);
                 u64* acco = acc + ((size_t)o << P::LOGS);
@@ -253,18 +276,22 @@ k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const dou
             group_sync(bar_id, NT);
             GROUP_PROF(6)
         }
-        // ---- sample extract coefficient 0
+        // ---- sample extract coefficient 0 (extended: coefficients 0..nout-1)
         {
-            u64* o = out + (size_t)ct * ((size_t)N + 1);
-            for (int w = tid; w < 2 * S; w += NT) {
-                const int c = w >> P::LOGS, s = w & (S - 1);
-                const int j = slot_to_coef<P>(s, 0);
-                const u64 v = acc[w];
-                if (c < 1) {
-                    if (j == 0) o[0] = v;
-                    else o[N - j] = 0ULL - v;
-                } else if (j == 0)
-                    o[N] = v;
+            const int nout = EXT ? g.nout : 1;
+            for (int u = 0; u < nout; u++) {
+                // coefficient u of the product: mask word t is A[u - t] (t <= u), -A[N + u - t] (t > u)
+                u64* o = out + ((size_t)ct * nout + u) * ((size_t)N + 1);
+                for (int w = tid; w < 2 * S; w += NT) {
+                    const int c = w >> P::LOGS, s = w & (S - 1);
+                    const int j = slot_to_coef<P>(s, 0);
+                    const u64 v = acc[w];
+                    if (c < 1) {
+                        if (j <= u) o[u - j] = v;
+                        else o[N + u - j] = 0ULL - v;
+                    } else if (j == u)
+                        o[N] = v;
+                }
             }
         }
         group_sync(bar_id, NT);              // the next round re-initialises the accumulator

@@ -324,6 +324,7 @@ struct TwCtx {
     unsigned base;            // tensor-memory allocation base (for dealloc)
     unsigned tA, tB;          // this thread's mid-pass twiddles in tensor memory (TMEM_TW plans)
     unsigned tAcc;            // this thread's accumulator words in tensor memory (ACC_TM plans)
+    unsigned tT;              // this thread's R1 stage-1 twiddles in tensor memory (k_pbs_group: one item per thread)
     const double2 *sA, *sB;   // mid-pass twiddle tables in shared memory (other plans)
     const double2* twT;       // stage-1 twiddles [R1][L1] in global memory (L1/L2 resident)
 };
@@ -352,7 +353,7 @@ __device__ __forceinline__ TwCtx tw_setup(double2* tw_smem, const double2* __res
     tw.twT = twT;
     tw.sA = tw_smem;
     tw.sB = tw_smem + P::TWA;
-    tw.base = tw.tA = tw.tB = tw.tAcc = 0;
+    tw.base = tw.tA = tw.tB = tw.tAcc = tw.tT = 0;
     if constexpr (P::TMEM_TW) {
         __shared__ unsigned s_tmem_base;
         const int warp = threadIdx.x >> 5;
@@ -532,10 +533,14 @@ __device__ __forceinline__ void stage1_gather_local(const double2* recv, int j2,
     for (int j1 = 0; j1 < P::R1; j1++) z[j1] = (j1 == 0) ? v[0] : cmulc(v[j1], g.cj[j1]);
 }
 
-template <class P>
+template <class P, bool TMT = false /* the thread's only item: twiddles wait in its tensor-memory lane */>
 __device__ __forceinline__ void load_T(double2* T, const TwCtx& tw, int j2) {
+    if constexpr (TMT) {
+        tmem_load_c<P::R1>(tw.tT, T);
+    } else {
 #pragma unroll
-    for (int t1 = 0; t1 < P::R1; t1++) T[t1] = __ldg(&tw.twT[((size_t)t1 << P::LOGL1) + j2]);
+        for (int t1 = 0; t1 < P::R1; t1++) T[t1] = __ldg(&tw.twT[((size_t)t1 << P::LOGL1) + j2]);
+    }
 }
 
 // slot (index inside one polynomial's CTA slice) -> coefficient index
@@ -555,7 +560,7 @@ __device__ __forceinline__ size_t ggsw_slice(int j, int o, int k, int rank) {
 // ---- P1 of a CMUX for every item (c, q) of this CTA: diff = X^a * ACC - ACC, signed decomposition
 // (closest representable, balanced digits), one stage-1 emit per level.  ST = u32 when the kept
 // level*base_log bits fit 30 bits (halves the registers of the decomposition state).
-template <class P, typename ST>
+template <class P, typename ST, bool TMT = false>
 __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* __restrict__ work, int rank, int a,
                                          const PbsGeom& g, const TwCtx& tw,
                                          int tix = -1 /* thread index inside the NT threads of this ciphertext (default: threadIdx.x) */) {
@@ -573,7 +578,7 @@ __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* _
         const int j2 = (rank << P::LOGQ) + q;
         const u64* accc = acc + ((size_t)c << P::LOGS);
         double2 T[R1];
-        load_T<P>(T, tw, j2);
+        load_T<P, TMT>(T, tw, j2);
         ST st[2 * R1];
         {
             // coefficient hj*L1 + j2 of X^a * ACC is +-ACC[(hj*L1 + j2 - a) mod 2N]: the low bits (owner CTA
@@ -1372,10 +1377,20 @@ struct PbsPlanOps {
         if constexpr (P::GROUP > 1) {
             // fhe_pbs_set_group(0) / FHE_PBS_GROUP=0 run the plan's generic kernel instead (bit-identical outputs)
             using GP = PbsGroup<P, P::GROUP>;
-            const bool plain = !(a.bsk_ct_stride || a.g.nout > 1 || a.g.theta > 0);
-            if (g_pbs_group != 0 && plain && a.g.k == 1 && GP::smem(a.g) + 2048 <= PBS_SMEM_MAX)
-                return launch_grouped(k_pbs_group<P, P::GROUP>, GP::NTC, GP::smem(a.g), a.B, a.st, a.out, a.in, a.B, a.bskF,
-                                      a.luts, a.lut_idx, a.g, a.twT, a.tw_mid, a.prof);
+            const bool ext = a.bsk_ct_stride || a.g.nout > 1 || a.g.theta > 0;
+            // g_pbs_group: 1 = two slots per CTA, GGSW_i streamed from L2 (default: measured fastest); 2 = GGSW_i staged once
+            // per SM in the shared-memory ring when it fits (north-star design, measured 4 % slower); 0 = k_pbs
+            const bool ring = g_pbs_group == 2 && !ext && GP::smem(a.g, true) + 2048 <= PBS_SMEM_MAX;
+            if (g_pbs_group != 0 && a.g.k == 1 && GP::smem(a.g, ring) + 2048 <= PBS_SMEM_MAX) {
+                if (ring)
+                    return launch_grouped(k_pbs_group<P, P::GROUP, true, false>, GP::NTC, GP::smem(a.g, true), a.B, a.st, a.out,
+                                          a.in, a.B, a.bskF, a.luts, a.lut_idx, a.g, a.twT, a.tw_mid, a.prof, (size_t)0);
+                if (ext)
+                    return launch_grouped(k_pbs_group<P, P::GROUP, false, true>, GP::NTC, GP::smem(a.g, false), a.B, a.st, a.out,
+                                          a.in, a.B, a.bskF, a.luts, a.lut_idx, a.g, a.twT, a.tw_mid, a.prof, a.bsk_ct_stride);
+                return launch_grouped(k_pbs_group<P, P::GROUP, false, false>, GP::NTC, GP::smem(a.g, false), a.B, a.st, a.out,
+                                      a.in, a.B, a.bskF, a.luts, a.lut_idx, a.g, a.twT, a.tw_mid, a.prof, (size_t)0);
+            }
         }
         if constexpr (P::PIPE) {
             // fhe_pbs_set_pipeline(0) / FHE_PBS_PIPE=0 run the plan's generic kernel instead: both kernels perform the same

@@ -142,7 +142,8 @@ int fhe_pbs_set_profile(long long* dev_buf);
 /* test / measurement hook: 0 makes the pipelined bootstrap plans (k_pbs_pipe) run their generic kernel; returns the
  * previous setting.  Both kernels are bit-identical by construction; not part of the reference-facing surface */
 int fhe_pbs_set_pipeline(int enabled);
-/* the same switch for the grouped plans (k_pbs_group: several ciphertexts per CTA, each GGSW staged once per SM) */
+/* the same switch for the grouped plans (k_pbs_group: two ciphertexts per CTA at N = 2048, twiddles in tensor memory):
+ * 0 = k_pbs, 1 = grouped with GGSW_i streamed from L2 (default), 2 = grouped with GGSW_i staged once per SM in shared memory */
 int fhe_pbs_set_group(int enabled);
 
 /* ---- torus linear algebra on [E][L] tensors (L = kN+1) --------------------------------

@@ -307,15 +307,18 @@ def test_pipelined_bootstrap_is_bit_identical_to_the_generic_kernel(cuda_device,
         assert bad.size == 0, (bad[:8].tolist(), int(bad.size))
 
 
-@pytest.mark.parametrize("B", [1, 100, 148, 149, 296, 300, 1000])
-def test_grouped_bootstrap_is_bit_identical_to_the_generic_kernel(cuda_device, B):
-    """k_pbs_group (pbs_group.cuh: one CTA per SM carries two N = 2048 ciphertexts, every GGSW_i is staged once per SM by a
-    bulk copy and shared by both) performs the floating-point operations of k_pbs in the same order: every output WORD must
-    be equal (fhe_pbs_set_group switches at run time).  The batch sizes cover one slot per CTA, ragged second slots, and
-    several rounds with a ragged last one (the ring of staged GGSWs runs on across rounds)."""
+@pytest.mark.parametrize("B,level,base_log", [(1, 1, 23), (100, 1, 23), (148, 1, 23), (149, 1, 23), (296, 1, 23),
+                                              (300, 1, 23), (1000, 1, 23), (300, 2, 12), (449, 3, 8)])
+def test_grouped_bootstrap_is_bit_identical_to_the_generic_kernel(cuda_device, B, level, base_log):
+    """k_pbs_group (pbs_group.cuh: one CTA per SM carries two N = 2048 ciphertexts; mode 1 streams GGSW_i from L2, mode 2
+    stages it once per SM by bulk copies into a shared-memory ring read by both) performs the floating-point operations of
+    k_pbs in the same order: every output WORD must be equal (fhe_pbs_set_group switches at run time).  The batch sizes
+    cover one slot per CTA, ragged second slots, and several rounds with a ragged last one (the ring runs on across
+    rounds).  With two levels the GGSW does not fit next to two ciphertexts (mode 2 streams as well); three levels run
+    another plan (the switch is a no-op there)."""
     stress = os.environ.get("CNP_B200_STRESS", "0") not in ("", "0")
     n = 742 if stress else 96
-    p = E.CryptoParams(p=4, n=n, k=1, N=2048, pbs_level=1, pbs_base_log=23, ks_level=5, ks_base_log=3,
+    p = E.CryptoParams(p=4, n=n, k=1, N=2048, pbs_level=level, pbs_base_log=base_log, ks_level=5, ks_base_log=3,
                        lwe_std=2.0 ** -40, glwe_std=2.0 ** -52)
     ks = E.KeySet(p, cuda_device, seed=22)
     ev = E.EvalKeys.of(ks)
@@ -329,6 +332,8 @@ def test_grouped_bootstrap_is_bit_identical_to_the_generic_kernel(cuda_device, B
     prev = lib.fhe_pbs_set_group(1)
     try:
         grouped = [E.to_np_u64(E.bootstrap(ev, small, luts, lut_idx)) for _ in range(2)]
+        lib.fhe_pbs_set_group(2)
+        grouped.append(E.to_np_u64(E.bootstrap(ev, small, luts, lut_idx)))
         lib.fhe_pbs_set_group(0)
         generic = E.to_np_u64(E.bootstrap(ev, small, luts, lut_idx))
     finally:
