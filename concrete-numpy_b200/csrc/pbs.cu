@@ -179,6 +179,34 @@ static int get_plan(int n, int k, int N, int level, int base_log, int variant, c
     return 0;
 }
 
+// Wave-alignment counters of the pipelined bootstrap: a small per-device pool, one zeroed slot per launch (launches on
+// different streams may overlap; a shared counter would only cost them their alignment, never correctness)
+static int g_pbs_wave = [] { const char* e = getenv("FHE_PBS_WAVE"); return (e && e[0] == '0') ? 0 : 1; }();
+int pbs_wave_counter(cudaStream_t st, unsigned** ctr) {
+    *ctr = nullptr;
+    if (!g_pbs_wave) return 0;
+    constexpr int SLOTS = 64;
+    static std::map<int, unsigned*> pools;
+    static std::map<int, unsigned> next;
+    int dev = 0;
+    FHE_CUDA(cudaGetDevice(&dev));
+    unsigned* slot = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_plan_mu);
+        auto it = pools.find(dev);
+        if (it == pools.end()) {
+            unsigned* p = nullptr;
+            FHE_CUDA(cudaMalloc(&p, SLOTS * 64));            // one 64-byte line per slot
+            it = pools.emplace(dev, p).first;
+            next[dev] = 0;
+        }
+        slot = it->second + 16 * (next[dev]++ % SLOTS);
+    }
+    FHE_CUDA(cudaMemsetAsync(slot, 0, sizeof(unsigned), st));
+    *ctr = slot;
+    return 0;
+}
+
 static long long* g_prof_buf = nullptr;
 int g_pbs_pipeline = [] { const char* e = getenv("FHE_PBS_PIPE"); return (e && e[0] == '0') ? 0 : 1; }();
 int g_pbs_group = [] { const char* e = getenv("FHE_PBS_GROUP"); return e ? atoi(e) : 1; }();

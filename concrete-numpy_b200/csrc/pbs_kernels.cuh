@@ -1299,6 +1299,8 @@ static int launch_clustered(Kern kern, int C, int NT, int tmem_cols, size_t smem
 }
 
 extern int g_pbs_pipeline;    // pbs.cu: k_pbs_pipe enabled (default 1, FHE_PBS_PIPE=0 / fhe_pbs_set_pipeline)
+// pbs.cu: a zeroed device counter for the wave alignment of one k_pbs_pipe launch (null when FHE_PBS_WAVE=0)
+int pbs_wave_counter(cudaStream_t st, unsigned** ctr);
 extern int g_pbs_group;       // pbs.cu: k_pbs_group enabled (default 1, FHE_PBS_GROUP=0 / fhe_pbs_set_group)
 
 // one CTA per SM, GROUP ciphertexts per CTA (k_pbs_group)
@@ -1398,9 +1400,13 @@ struct PbsPlanOps {
             const bool use_pipe = g_pbs_pipeline != 0;
             const bool plain = !(a.bsk_ct_stride || a.g.nout > 1 || a.g.theta > 0);
             const bool fits = use_pipe && plain && a.g.k == 1 && a.g.level == 2 && 2 * a.g.base_log <= 30 && a.g.base_log >= 2;
-            if (fits)
+            if (fits) {
+                unsigned* wave_ctr = nullptr;
+                const int rc = pbs_wave_counter(a.st, &wave_ctr);
+                if (rc) return rc;
                 return launch_clustered(k_pbs_pipe<P>, P::C, P::NT, P::TM_CTA, smem_pipe(), a.B, a.st, a.out, a.in, a.B,
-                                        a.bskF, a.luts, a.lut_idx, a.g, a.twT, a.tw_mid, a.prof);
+                                        a.bskF, a.luts, a.lut_idx, a.g, a.twT, a.tw_mid, a.prof, wave_ctr);
+            }
         }
         if (a.bsk_ct_stride || a.g.nout > 1 || a.g.theta > 0)
             return launch_clustered(k_pbs<P, true>, P::C, P::NT, P::TM_CTA, smem_pbs(a.g), a.B, a.st, a.out, a.in, a.B,

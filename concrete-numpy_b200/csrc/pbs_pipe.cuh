@@ -122,7 +122,8 @@ template <class P>
 __global__ void __launch_bounds__(P::NT, 1)
 k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* __restrict__ bskF,
            const u64* __restrict__ luts, const int* __restrict__ lut_idx, const PbsGeom g,
-           const double2* __restrict__ twT, const double2* __restrict__ tw_mid, long long* prof) {
+           const double2* __restrict__ twT, const double2* __restrict__ tw_mid, long long* prof,
+           unsigned* __restrict__ wave_ctr /* zeroed per launch, or null: no wave alignment */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int C = P::C, R1 = P::R1, NT = P::NT, RF = P::RF, BUF = P::BUF, Q = P::Q, S = P::S;
     constexpr int N = P::N;
@@ -175,6 +176,19 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
         tmem_wait_st();
     }
     for (long ct = cluster_id; ct < B; ct += nclusters) {
+        if (wave_ctr != nullptr && rank == 0 && tid == 0) {
+            // Wave alignment: the key (2 GiB at N = 32768) streams from HBM once per WAVE of resident clusters only while
+            // they stay within an L2's worth of CMUX iterations of each other (2.1 MB per iteration, 126 MB of L2); left
+            // alone they drift apart over a launch and re-fetch slices a faster cluster already evicted (measured 1.9x the
+            // key bytes).  Every cluster counts itself in before a new ciphertext and waits for the rest of its wave; the
+            // wait is bounded (clusters that are not co-resident -- another kernel on the device -- must not deadlock).
+            const long wave = (ct - cluster_id) / nclusters;
+            const long want = (wave + 1) * nclusters;
+            const unsigned target = (unsigned)(want < B ? want : B);
+            atomicAdd(wave_ctr, 1u);
+            const long long t_end = clock64() + 4000000LL;
+            while (*reinterpret_cast<volatile unsigned*>(wave_ctr) < target && clock64() < t_end) __nanosleep(256);
+        }
         const u64* lwe = in + (size_t)ct * (g.n + 1);
         const u64* lut = luts + (size_t)(lut_idx ? lut_idx[ct] : 0) * 2 * N;
         int a_next = modswitch(lwe[0], g.logN);
