@@ -35,10 +35,6 @@ __device__ __forceinline__ unsigned smem_atom_inc_acq_rel(unsigned* p) {
     asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
     return old;
 }
-__device__ __forceinline__ void bulk_copy_from_global(void* dst_smem, const void* src, unsigned bytes, u64* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 template <class P, int G>
 struct PbsGroup {

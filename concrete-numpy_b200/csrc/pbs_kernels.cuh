@@ -262,6 +262,11 @@ __device__ __forceinline__ void bulk_copy_to_cluster(unsigned dst_cluster_addr, 
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_cluster_addr), "r"(smem_u32(src)), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
 }
+// global -> this CTA's shared memory, completion (bytes) on a local mbarrier
+__device__ __forceinline__ void bulk_copy_from_global(void* dst_smem, const void* src, unsigned bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // relaxed: the arrival only says "my READS of the spare buffers are done" (their values were consumed before
 // the preceding __syncthreads), so no memory fence (MEMBAR.ALL.GPU) is needed
@@ -1374,7 +1379,7 @@ struct PbsPlanOps {
         if (per_sm > 512 / P::TM_CTA) per_sm = 512 / P::TM_CTA;
         return per_sm * sms;
     }
-    static size_t smem_pipe() { return (size_t)2 * P::S * 8 + (size_t)5 * P::BUF * 16; }
+    static size_t smem_pipe() { return PipeStage<P>::SMEM; }
     static int pbs(const PbsLaunchArgs& a) {
         if constexpr (P::GROUP > 1) {
             // fhe_pbs_set_group(0) / FHE_PBS_GROUP=0 run the plan's generic kernel instead (bit-identical outputs)

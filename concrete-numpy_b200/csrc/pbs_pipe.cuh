@@ -118,6 +118,20 @@ __device__ __forceinline__ void pipe_send(const double2* stg, double2* dst_buf, 
                          (unsigned)(sizeof(double2) << P::LOGQ), mapa_u32(smem_u32(bar), d));
 }
 
+// GGSW staging of the pipelined kernel: on when two stages of the CTA's 8 slices fit next to its buffers
+template <class P>
+struct PipeStage {
+    static constexpr size_t BASE = (size_t)2 * P::S * 8 + (size_t)5 * P::BUF * 16;
+    static constexpr size_t RING = (size_t)2 * 8 * P::BUF * 16;
+    static constexpr bool ON = BASE + RING + 4096 <= PBS_SMEM_MAX;
+    static constexpr size_t SMEM = BASE + (ON ? RING : 0);
+};
+template <bool SMEM_SRC>
+__device__ __forceinline__ double2 pipe_ld(const double2* p) {
+    if constexpr (SMEM_SRC) return *p;
+    else return __ldg(p);
+}
+
 template <class P>
 __global__ void __launch_bounds__(P::NT, 1)
 k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* __restrict__ bskF,
@@ -144,6 +158,13 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
     u64* ra = reinterpret_cast<u64*>(smem_raw);                        // [2][S] rotated accumulator of the coming CMUX
     double2* work = reinterpret_cast<double2*>(ra + 2 * (size_t)S);    // [4][BUF]
     double2* xstg = work + 4 * (size_t)BUF;                            // [BUF] spare staging buffer
+    // Plans with small local transforms (the latency plans: one ciphertext on several SMs, a handful of warps per SM) leave
+    // most of the shared memory free and cannot hide the L2 latency of the key behind other warps: the fused pass spent
+    // 3.3 k of 12 k cycles per CMUX waiting for its GGSW values (N = 4096 on 4 CTAs).  There the CTA's 8 slices of GGSW_{i+1}
+    // are fetched by bulk copies into a two-stage ring while CMUX i runs, and the fused pass reads shared memory.
+    constexpr bool STG = PipeStage<P>::ON;
+    double2* gst = xstg + (size_t)BUF;                                 // [2][8][BUF] staged GGSW slices (STG plans)
+    __shared__ __align__(8) u64 s_gbar[2];    // staged GGSW of ring stage s has landed
     __shared__ __align__(8) u64 s_bar[8];     // 0..3: forward data of work buffer b; 4, 5: inverse data of output o; 6, 7: rotated polynomial c
     const int tid = threadIdx.x;
     const int rank = (int)cg::this_cluster().block_rank();
@@ -156,6 +177,7 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
     const TwCtx tw = tw_setup<P>(nullptr, twT, tw_mid);
     if (tid == 0) {
         for (int b = 0; b < 8; b++) mbar_init(&s_bar[b], 1);
+        for (int b = 0; b < 2; b++) mbar_init(&s_gbar[b], 1);
         mbar_fence_init();
         for (int b = 0; b < 6; b++) mbar_arm(&s_bar[b], BUF_BYTES);    // first CMUX: forward and inverse data
     }
@@ -163,6 +185,15 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
     cg::this_cluster().sync();                // every CTA's barriers exist before the first remote access
     cluster_arrive();                         // pairs with the wait of the first CMUX ("previous CMUX finished everywhere")
     unsigned ph = 0;
+    unsigned gph = 0;                                  // bit s: parity the next wait on s_gbar[s] uses
+    // thread t < 8 issues slice t = 2 * j + o of GGSW_i for this rank into ring stage `stage`
+    auto stage_ggsw = [&](int i, int stage) {
+        if (tid == 0) mbar_arm(&s_gbar[stage], 8 * BUF_BYTES);
+        __syncwarp();
+        if (tid < 8)
+            bulk_copy_from_global(gst + ((size_t)(stage * 8 + tid) << P::LOGBUF),
+                                  bskF + (size_t)i * ggsw_stride + (((size_t)tid * C + rank) << P::LOGBUF), BUF_BYTES, &s_gbar[stage]);
+    };
     const int j2_0 = (rank << P::LOGQ) + tid;         // item ii of this thread: q = tid + ii * NT, j2 = j2_0 + ii * NT
     // the stage-1 twiddles of this thread's items never change: they live in the tensor-memory columns the plan leaves free
     constexpr int TM_SLOTS = (NT + 127) / 128;       // thread slots per tensor-memory lane
@@ -225,14 +256,20 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
             mbar_arrive(&s_bar[6]);
             mbar_arrive(&s_bar[7]);
         }
+        if constexpr (STG) {
+            if (tid < 32) stage_ggsw(0, 0);   // both stages are free: every fused pass of the previous ciphertext is over
+        }
 
         for (int i = 0; i < g.n; i++) {
             const bool push = (i + 1 < g.n);
             a_next = push ? modswitch(lwe_ahead, g.logN) : 0;
             if (i + 2 < g.n) lwe_ahead = lwe[i + 2];
-            // GGSW_{i+1} slices of this rank -> L2 one iteration ahead
-            if (push && tid < 8)
-                prefetch_l2_bulk(bskF + (size_t)(i + 1) * ggsw_stride + (((size_t)tid * C + rank) << P::LOGBUF), BUF_BYTES);
+            // GGSW_{i+1} slices of this rank: into the other ring stage (its readers finished with the fused pass of CMUX
+            // i - 1, a __syncthreads ago), or into L2 one iteration ahead
+            if constexpr (!STG) {
+                if (push && tid < 8)
+                    prefetch_l2_bulk(bskF + (size_t)(i + 1) * ggsw_stride + (((size_t)tid * C + rank) << P::LOGBUF), BUF_BYTES);
+            }
             // ---------------- P1: decompose X^a * ACC - ACC, stage 1, bulk copies to the owners
             {
                 double2 T[IPT * R1];
@@ -284,6 +321,12 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 fence_proxy_async();                 // every writer: its staged values must be visible to the copy engine
                 __syncthreads();
                 if (tid < C) pipe_send<P>(xstg, work + (size_t)BUF, &s_bar[1], rank, tid, g.dbg & 2);
+                // staged GGSW_{i+1}: issued BEHIND the last forward send -- the copy engine serves its queue in order, and
+                // 64 KiB from L2 / HBM ahead of the sends delayed every one of them (measured: P1 +1.4 k cycles per CMUX);
+                // the next latency-critical copies (the inverse exchange) are three phases away
+                if constexpr (STG) {
+                    if (push && tid < 32) stage_ggsw(i + 1, (i + 1) & 1);
+                }
             }
             PIPE_PROF(0)
             // ---------------- P2: forward mid passes, polynomial 0 while polynomial 1 is still in flight
@@ -300,8 +343,13 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 for (int b = 0; b < 4; b++) mbar_arm(&s_bar[b], BUF_BYTES);      // next CMUX
             mid_pass<P::LRA, P::LOGL1, P::LOGBUF, NT, false, true>(work + BUF, 2, tw.tA, tw.sA, 2);
             __syncthreads();
-            const double2* gp = bskF + (size_t)i * ggsw_stride + ((size_t)rank << P::LOGBUF);
-            const size_t o_stride = (size_t)C << P::LOGBUF;
+            const double2* gp = STG ? gst + ((size_t)((i & 1) * 8) << P::LOGBUF)
+                                    : bskF + (size_t)i * ggsw_stride + ((size_t)rank << P::LOGBUF);
+            const size_t o_stride = STG ? (size_t)BUF : (size_t)C << P::LOGBUF;
+            if constexpr (STG) {
+                mbar_wait(&s_gbar[i & 1], (gph >> (i & 1)) & 1u);
+                gph ^= 1u << (i & 1);
+            }
             if constexpr (NG == NT) {
                 // the GGSW values of the first digit polynomial are requested before the last mid pass: their L2 latency
                 // hides behind it instead of opening the multiply-accumulate
@@ -310,7 +358,7 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
 #pragma unroll
                 for (int o = 0; o < 2; o++)
 #pragma unroll
-                    for (int m = 0; m < RF; m++) gv[o][m] = __ldg(gp + o * o_stride + m * NG);
+                    for (int m = 0; m < RF; m++) gv[o][m] = pipe_ld<STG>(gp + o * o_stride + m * NG);
                 if constexpr (P::LRB > 0) {
                     mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, NT, false, true>(work + BUF, 2, tw.tB, tw.sB, 2);
                     __syncthreads();
@@ -340,7 +388,7 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                             r[o][m].x = fma(-x[m].y, b.y, r[o][m].x);
                             r[o][m].y = fma(x[m].x, b.y, r[o][m].y);
                             r[o][m].y = fma(x[m].y, b.x, r[o][m].y);
-                            if (more) gv[o][m] = __ldg(gn + o * o_stride + m * NG);
+                            if (more) gv[o][m] = pipe_ld<STG>(gn + o * o_stride + m * NG);
                         }
                 }
 #pragma unroll
@@ -358,7 +406,7 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                 gp += w + (size_t)o * o_stride;
                 double2 gv[RF];
 #pragma unroll
-                for (int m = 0; m < RF; m++) gv[m] = __ldg(gp + m * NG);
+                for (int m = 0; m < RF; m++) gv[m] = pipe_ld<STG>(gp + m * NG);
                 if constexpr (P::LRB > 0) {
                     mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, NT, false, true>(work + BUF, 2, tw.tB, tw.sB, 2);
                     __syncthreads();
@@ -383,7 +431,7 @@ k_pbs_pipe(u64* __restrict__ out, const u64* __restrict__ in, long B, const doub
                         r[m].x = fma(-x[m].y, b.y, r[m].x);
                         r[m].y = fma(x[m].x, b.y, r[m].y);
                         r[m].y = fma(x[m].y, b.x, r[m].y);
-                        if (more) gv[m] = __ldg(gn + m * NG);
+                        if (more) gv[m] = pipe_ld<STG>(gn + m * NG);
                     }
                 }
                 Dft<RF, true>::run(r);

@@ -10,10 +10,13 @@ NAMES = ["P1 decomp+stage1", "sync A", "mid fwd", "fused MAC", "mid inv", "sync 
 # "w" = the bootstrap of the 16-bit wide lookup (N = 2048, 3 levels, 256-thread plan), run as a 4-bit bootstrap
 WIDE_PBS = E.CryptoParams(p=4, n=644, k=1, N=2048, pbs_level=3, pbs_base_log=11, ks_level=4, ks_base_log=3,
                           lwe_std=2.0 ** -14.5, glwe_std=2.0 ** -51.6)
-for pbits, B in ((8, 36), (6, 148), (4, 888), ("w", 444)):
+P5 = E.CryptoParams(p=5, n=786, k=1, N=4096, pbs_level=2, pbs_base_log=13, ks_level=5, ks_base_log=3,
+                    lwe_std=2.0 ** -20, glwe_std=2.0 ** -50)
+VARIANT = int(os.environ.get("PHASE_VARIANT", "0"))      # plan variant (latency plans: larger clusters)
+for pbits, B in ((8, 36), (6, 148), (4, 888), ("w", 444), (5, int(os.environ.get("PHASE_B", "148")))):
     if len(sys.argv) > 1 and str(pbits) not in sys.argv[1:]:
         continue
-    p = WIDE_PBS if pbits == "w" else REFERENCE_SETS[pbits]
+    p = WIDE_PBS if pbits == "w" else P5 if pbits == 5 else REFERENCE_SETS[pbits]
     ks = E.KeySet(p, dev, seed=1)
     ev = E.EvalKeys.of(ks)
     rng = np.random.default_rng(0)
@@ -21,12 +24,12 @@ for pbits, B in ((8, 36), (6, 148), (4, 888), ("w", 444)):
     table = rng.integers(0, 1 << p.p, (1, 1 << p.p))
     luts = E.from_np_u64(E.build_lut_accumulators(p, table), dev)
     small = E.keyswitch(ev, E.encrypt(ks, m))
-    E.bootstrap(ev, small, luts, None)
+    E.bootstrap(ev, small, luts, None, variant=VARIANT)
     prof = torch.zeros(256, dtype=torch.int64, device=dev)
     _lib.call("fhe_pbs_set_profile", prof.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    out = E.bootstrap(ev, small, luts, None)
+    out = E.bootstrap(ev, small, luts, None, variant=VARIANT)
     e1.record()
     torch.cuda.synchronize()
     _lib.call("fhe_pbs_set_profile", None)
@@ -39,7 +42,7 @@ for pbits, B in ((8, 36), (6, 148), (4, 888), ("w", 444)):
     for nm, v in zip(NAMES, c):
         print(f"   {nm:18s} {v / max(c.sum(), 1) * 100:5.1f}%   {v / 1e3:10.0f} kcycles")
     allp = prof.cpu().numpy().reshape(16, 16).astype(np.float64)
-    C = max(1, _lib.load().fhe_pbs_cluster_size(p.N, p.k, p.pbs_level))
+    C = max(1, ev.variant_clusters[VARIANT])
     if C > 1:
         print("   per-rank kcycles of cluster 0 (P1 | syncA | midF | fused | midI | syncB | P5 | syncC):")
         for r in range(min(C, 16)):
