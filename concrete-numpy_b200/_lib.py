@@ -37,6 +37,7 @@ _SIGS = {
     "fhe_pbs_batch": (C.c_int, [_p, _p, C.c_long, _p, _p, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_pbs_num_variants": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "fhe_pbs_variant_pipelined": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fhe_pbs_variant_grouped": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "fhe_pbs_variant_cluster_size": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "fhe_pbs_variant_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "fhe_pbs_variant_capacity": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),

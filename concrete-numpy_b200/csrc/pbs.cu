@@ -293,6 +293,19 @@ int fhe_pbs_variant_pipelined(int N, int k, int level, int variant) {
     return plans[fit[variant]].meta.acctm == 2 ? 1 : 0;
 }
 
+// 1 if k = 1 bootstraps of this variant run the grouped kernel (k_pbs_group: one CTA per SM with several ciphertext slots --
+// also the lowest-latency plan of its size: a lone ciphertext has the SM and its tensor memory to itself), 0 if not
+int fhe_pbs_variant_grouped(int N, int k, int level, int variant) {
+    static const std::vector<PbsPlanEntry> plans = all_plans();
+    const std::vector<int> fit = fitting_plans(N, k, level);
+    if (variant < 0 || variant >= (int)fit.size()) return -1;
+    const PbsPlanMeta& m = plans[fit[variant]].meta;
+    if (m.group <= 1 || k != 1 || g_pbs_group == 0) return 0;
+    const size_t M = (size_t)1 << m.logM;
+    const size_t smem = (size_t)m.group * ((size_t)(k + 1) * 2 * M * 8 + (size_t)(k + 1) * level * M * 16);
+    return smem + 2048 <= PBS_SMEM_MAX ? 1 : 0;
+}
+
 // how many ciphertexts variant `variant` bootstraps concurrently on the current device (one wave)
 int fhe_pbs_variant_capacity(int N, int k, int level, int variant) {
     static const std::vector<PbsPlanEntry> plans = all_plans();

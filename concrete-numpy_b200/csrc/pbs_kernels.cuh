@@ -100,6 +100,7 @@ struct PbsPlan {
 struct PbsPlanMeta {       // what the host needs to know about a plan
     int C, logR1, lra, lrb, lrf, NT, minb, kmax, logM;
     int acctm;             // 1: accumulator in tensor memory + pushed rotated copy (PbsPlan::ACC_TM), 2: and k_pbs_pipe
+    int group;             // > 1: k = 1 bootstraps run k_pbs_group with this many ciphertext slots per CTA (when they fit)
     long smem_fixed;       // bytes of shared memory besides ACC and the work buffers (twiddles live in TMEM)
 };
 
@@ -1345,7 +1346,7 @@ template <class P>
 struct PbsPlanOps {
     static PbsPlanMeta meta() {
         return PbsPlanMeta{P::C, P::LOGR1, P::LRA, P::LRB, P::LRF, P::NT, P::MINB, P::KMAX, P::LOGM, P::PIPE ? 2 : (P::ACC_TM ? 1 : 0),
-                           (long)sizeof(double2) * P::TW_SMEM};
+                           P::GROUP, (long)sizeof(double2) * P::TW_SMEM};
     }
     static size_t smem_pbs(const PbsGeom& g) {
         return (size_t)(g.k + 1) * P::S * 8 + (size_t)g.J * P::BUF * 16 + (size_t)P::TW_SMEM * 16;

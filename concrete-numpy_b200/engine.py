@@ -223,6 +223,12 @@ class EvalKeys:
             self._pipelined = [p.k == 1 and p.pbs_level == 2 and 2 * p.pbs_base_log <= 30 and
                                lib.fhe_pbs_variant_pipelined(p.N, p.k, p.pbs_level, v) == 1
                                for v in range(len(self.variant_clusters))]
+            self._grouped0 = lib.fhe_pbs_variant_grouped(p.N, p.k, p.pbs_level, 0) == 1
+        # the grouped plan (k_pbs_group) is also the latency plan of its size: a lone ciphertext per SM has the SM and its
+        # tensor memory to itself (measured at N = 2048, scripts/variant_latency.py: 3.13 ms on one SM, 4.6 ms on a
+        # 2-CTA cluster, 3.96 ms on 4) -- as long as the batch leaves one slot per SM
+        if self._grouped0 and 0 < count <= self._capacity[0] // 2:
+            return 0
         best = 0
         for v, cap in enumerate(self._capacity):
             # 16-CTA clusters are a capacity fallback (N = 32768 with >= 3 levels), not a latency win

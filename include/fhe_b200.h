@@ -97,6 +97,8 @@ int fhe_pbs_batch(uint64_t* out /* [B][kN+1] */, const uint64_t* in /* [B][n+1] 
 int fhe_pbs_num_variants(int N, int k, int level);
 /* 1 if two-level k = 1 bootstraps of the variant run the pipelined kernel, 0 if not, < 0 if there is no such variant */
 int fhe_pbs_variant_pipelined(int N, int k, int level, int variant);
+/* 1 if k = 1 bootstraps of the variant run the grouped kernel (one CTA per SM, several ciphertext slots), 0 if not */
+int fhe_pbs_variant_grouped(int N, int k, int level, int variant);
 int fhe_pbs_variant_cluster_size(int N, int k, int level, int variant);
 /* plan of a variant: meta[0..7] = cluster size, log2 of the stage-1 / mid-pass A / mid-pass B / fused radices,
  * threads per CTA, minimum CTAs per SM, largest GLWE dimension (documentation / tests) */

@@ -263,7 +263,10 @@ def test_pbs_plan_variants_agree(cuda_device, p_bits, n, k, N, level, base_log):
     piped = [v for v, c in enumerate(ev.variant_clusters)
              if v > 0 and level == 2 and lib.fhe_pbs_variant_pipelined(N, k, level, v) == 1
              and 2 * c >= ev.variant_clusters[best] > c]
-    assert ev.variant_for_batch(1) == (piped[0] if piped else best) and ev.variant_for_batch(100000) == 0
+    # ... and the grouped plan (one CTA per SM, k_pbs_group) is the latency plan of its size (N = 2048, up to two levels)
+    grouped0 = lib.fhe_pbs_variant_grouped(N, k, level, 0) == 1
+    assert grouped0 == (N == 2048 and k == 1 and level <= 2)
+    assert ev.variant_for_batch(1) == (0 if grouped0 else piped[0] if piped else best) and ev.variant_for_batch(100000) == 0
     if N == 4096:
         assert piped and ev.variant_clusters[piped[0]] == 4
     assert all(c >= 1 for c in ev._capacity)
