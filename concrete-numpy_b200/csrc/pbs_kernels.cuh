@@ -1382,7 +1382,7 @@ struct PbsPlanOps {
     }
     static size_t smem_pipe() { return PipeStage<P>::SMEM; }
     static int pbs(const PbsLaunchArgs& a) {
-        if constexpr (P::GROUP > 1) {
+        if constexpr (P::GROUP >= 1) {
             // fhe_pbs_set_group(0) / FHE_PBS_GROUP=0 run the plan's generic kernel instead (bit-identical outputs)
             using GP = PbsGroup<P, P::GROUP>;
             const bool ext = a.bsk_ct_stride || a.g.nout > 1 || a.g.theta > 0;
