@@ -462,22 +462,23 @@ __device__ __forceinline__ void mid_pass(double2* __restrict__ work, int nbuf, u
 
 template <class P, bool INV>
 __device__ __forceinline__ void mid_passes(double2* work, int nbuf, const TwCtx& tw) {
+    constexpr int TMQ = (P::NT >= 512 && P::TMEM_TW) ? 4 : 0;      // 128-register plans fetch their twiddles 4 at a time
     if (!INV) {
         if constexpr (P::LRA > 0) {
-            mid_pass<P::LRA, P::LOGL1, P::LOGBUF, P::NT, false, P::TMEM_TW>(work, nbuf, tw.tA, tw.sA);
+            mid_pass<P::LRA, P::LOGL1, P::LOGBUF, P::NT, false, P::TMEM_TW, TMQ>(work, nbuf, tw.tA, tw.sA);
             __syncthreads();
         }
         if constexpr (P::LRB > 0) {
-            mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, P::NT, false, P::TMEM_TW>(work, nbuf, tw.tB, tw.sB);
+            mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, P::NT, false, P::TMEM_TW, TMQ>(work, nbuf, tw.tB, tw.sB);
             __syncthreads();
         }
     } else {
         if constexpr (P::LRB > 0) {
-            mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, P::NT, true, P::TMEM_TW>(work, nbuf, tw.tB, tw.sB);
+            mid_pass<P::LRB, P::LOGL1 - P::LRA, P::LOGBUF, P::NT, true, P::TMEM_TW, TMQ>(work, nbuf, tw.tB, tw.sB);
             __syncthreads();
         }
         if constexpr (P::LRA > 0) {
-            mid_pass<P::LRA, P::LOGL1, P::LOGBUF, P::NT, true, P::TMEM_TW>(work, nbuf, tw.tA, tw.sA);
+            mid_pass<P::LRA, P::LOGL1, P::LOGBUF, P::NT, true, P::TMEM_TW, TMQ>(work, nbuf, tw.tA, tw.sA);
             __syncthreads();
         }
     }

@@ -194,6 +194,7 @@ class EvalKeys:
         self.variant_clusters = [lib.fhe_pbs_variant_cluster_size(params.N, params.k, params.pbs_level, v)
                                  for v in range(max(n, 0))]
         self._capacity = None      # ciphertexts each variant bootstraps in one wave (queried on the device)
+        self._measured_best = {}   # batch size -> fastest variant, measured on first use (_calibrate)
         # tensor-core keyswitch (csrc/keyswitch_tc.cu): key bytes re-laid out once, on first use
         self.ks_tc_ok = (not params.linear_only) and bool(
             lib.fhe_ks_tc_supported(params.big_dim, params.n, params.ks_level, params.ks_base_log))
@@ -210,10 +211,13 @@ class EvalKeys:
         return self._ksk_tc
 
     def variant_for_batch(self, count: int) -> int:
-        """Plan variant for a batch of `count` ciphertexts: the largest cluster that still bootstraps them in a single
-        wave -- except that a PIPELINED variant (k_pbs_pipe: no cluster barriers) that holds the batch and is at most half
-        that cluster is faster (measured, scripts/variant_latency.py: N = 4096, 17 ciphertexts: 4.76 ms on 4 pipelined
-        CTAs vs 5.25 ms on 8; N = 8192: the pipelined plan has 2 CTAs and loses to 8)."""
+        """Plan variant for a batch of `count` ciphertexts.  More than one wave of the throughput plan: variant 0.  A
+        single wave: the variant measured fastest at this batch size (_calibrate, default).  With CNP_B200_VARIANT_CALIB=0 a
+        static rule instead: the largest cluster that still bootstraps the batch in a single wave -- except that the grouped
+        plan wins at its size and a PIPELINED variant (k_pbs_pipe) that holds the batch and is at most half that cluster is
+        faster (scripts/variant_latency.py: N = 4096, 17 ciphertexts: 4.4 ms on 4 pipelined CTAs vs 5.25 ms on 8)."""
+        if count > 0 and count in self._measured_best:
+            return self._measured_best[count]
         if self._capacity is None:
             lib = _lib.load()
             p = self.params
@@ -224,6 +228,11 @@ class EvalKeys:
                                lib.fhe_pbs_variant_pipelined(p.N, p.k, p.pbs_level, v) == 1
                                for v in range(len(self.variant_clusters))]
             self._grouped0 = lib.fhe_pbs_variant_grouped(p.N, p.k, p.pbs_level, 0) == 1
+        if count > self._capacity[0]:
+            return 0              # several waves of the throughput plan: nothing else competes
+        if count > 0 and len(self.variant_clusters) > 1 and os.environ.get("CNP_B200_VARIANT_CALIB", "1") not in ("", "0"):
+            return self._calibrate(count)
+        # static rule (CNP_B200_VARIANT_CALIB=0):
         # the grouped plan (k_pbs_group) is also the latency plan of its size: a lone ciphertext per SM has the SM and its
         # tensor memory to itself (measured at N = 2048, scripts/variant_latency.py: 3.13 ms on one SM, 4.6 ms on a
         # 2-CTA cluster, 3.96 ms on 4) -- as long as the batch leaves one slot per SM
@@ -238,6 +247,37 @@ class EvalKeys:
             if (v > 0 and v != best and self._pipelined[v] and 0 < count <= cap
                     and 2 * self.variant_clusters[v] >= self.variant_clusters[best] > self.variant_clusters[v]):
                 return v
+        return best
+
+    def _calibrate(self, count: int) -> int:
+        """Fastest plan variant for a single-wave batch of `count` ciphertexts, MEASURED the first time this batch size is
+        seen (one warm-up and one timed launch per variant on dummy ciphertexts, CUDA events; cached per size).  The wave
+        time of a variant depends on how its clusters share SMs, so no closed form picks reliably: at N = 4096, 60
+        ciphertexts take 9.1 ms on 1 CTA each, 11.0 on 2, 8.9 on 4 (two waves) and 7.0 on 8 (scripts/variant_latency.py).
+        A circuit has a handful of distinct batch sizes; each costs a few tens of milliseconds once per key set."""
+        p = self.params
+        dev = self.bsk_f.device
+        small = torch.zeros((count, p.n + 1), dtype=torch.int64, device=dev)
+        luts = torch.zeros((1, (p.k + 1) * p.N), dtype=torch.int64, device=dev)
+        out = torch.empty((count, p.ct_words), dtype=torch.int64, device=dev)
+        best, best_ms = 0, float("inf")
+        with torch.cuda.device(dev):
+            for v, c in enumerate(self.variant_clusters):
+                if c > 8 and v > 0:
+                    continue          # 16-CTA clusters are a capacity fallback, not a latency plan
+                bsk = self.bsk_for_variant(v).data_ptr()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                for timed in (False, True):
+                    if timed:
+                        e0.record()
+                    _lib.call("fhe_pbs_batch_variant", out.data_ptr(), small.data_ptr(), count, bsk, luts.data_ptr(), None,
+                              p.n, p.k, p.N, p.pbs_level, p.pbs_base_log, v, _stream())
+                e1.record()
+                e1.synchronize()
+                ms = e0.elapsed_time(e1)
+                if ms < 0.97 * best_ms:          # a later (larger) cluster must win clearly
+                    best, best_ms = v, ms
+        self._measured_best[count] = best
         return best
 
     def bsk_for_variant(self, v: int) -> torch.Tensor:

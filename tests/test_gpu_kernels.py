@@ -228,7 +228,7 @@ def test_pbs_matches_oracle(oracle, cuda_device, p_bits, n, k, N, level, base_lo
 @pytest.mark.parametrize("p_bits,n,k,N,level,base_log", [(3, 16, 1, 1024, 2, 10), (4, 20, 1, 2048, 1, 23),
                                                        (5, 16, 1, 4096, 2, 13), (6, 12, 1, 8192, 2, 13),
                                                        (7, 8, 1, 16384, 2, 15), (8, 8, 1, 32768, 2, 15)])
-def test_pbs_plan_variants_agree(cuda_device, p_bits, n, k, N, level, base_log):
+def test_pbs_plan_variants_agree(cuda_device, p_bits, n, k, N, level, base_log, monkeypatch):
     """Every plan variant (cluster size) of a parameter set bootstraps to the same messages from the
     Fourier BSK permuted into its layout (fhe_bsk_relayout), with the same noise level."""
     p = E.CryptoParams(p=p_bits, n=n, k=k, N=N, pbs_level=level, pbs_base_log=base_log, ks_level=8,
@@ -266,10 +266,44 @@ def test_pbs_plan_variants_agree(cuda_device, p_bits, n, k, N, level, base_log):
     # ... and the grouped plan (one CTA per SM, k_pbs_group) is the latency plan of its size (N = 2048, up to two levels)
     grouped0 = lib.fhe_pbs_variant_grouped(N, k, level, 0) == 1
     assert grouped0 == (N == 2048 and k == 1 and level <= 2)
+    monkeypatch.setenv("CNP_B200_VARIANT_CALIB", "0")           # the static rule (the default measures, see the next test)
     assert ev.variant_for_batch(1) == (0 if grouped0 else piped[0] if piped else best) and ev.variant_for_batch(100000) == 0
+    monkeypatch.delenv("CNP_B200_VARIANT_CALIB")
+    assert 0 <= ev.variant_for_batch(3) < len(ev.variant_clusters) and ev.variant_for_batch(100000) == 0
     if N == 4096:
         assert piped and ev.variant_clusters[piped[0]] == 4
     assert all(c >= 1 for c in ev._capacity)
+
+
+def test_variant_selection_is_measured(cuda_device):
+    """Single-wave batches run the plan variant that was FASTEST when that batch size was first seen (engine.EvalKeys.
+    _calibrate): at N = 4096 a lone ciphertext belongs on the pipelined 4-CTA plan, and the choice for 60 ciphertexts must
+    be at least as fast as the throughput plan measured here on the same batch."""
+    p = E.CryptoParams(p=5, n=786, k=1, N=4096, pbs_level=2, pbs_base_log=13, ks_level=5, ks_base_log=3,
+                       lwe_std=2.0 ** -20, glwe_std=2.0 ** -50)
+    ks = E.KeySet(p, cuda_device, seed=23)
+    ev = E.EvalKeys.of(ks)
+    table = np.arange(32)[None, :]
+    luts = E.from_np_u64(E.build_lut_accumulators(p, table), cuda_device)
+    m = (np.arange(60) % 32).astype(np.uint64)
+    small = E.keyswitch(ev, E.encrypt(ks, m))
+
+    def timed(v):
+        E.bootstrap(ev, small, luts, None, variant=v)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = E.bootstrap(ev, small, luts, None, variant=v)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), out
+
+    assert ev.variant_clusters[ev.variant_for_batch(1)] == 4
+    v60 = ev.variant_for_batch(60)
+    t_best, out = timed(v60)
+    t_0, _ = timed(0)
+    assert t_best <= 1.05 * t_0, (v60, t_best, t_0)
+    assert np.array_equal(E.decrypt(ks, out), m)
+    assert ev.variant_for_batch(60) == v60                       # cached
 
 
 @pytest.mark.parametrize("p_bits,N,base_log,cluster", [(8, 32768, 15, 8), (7, 16384, 15, 4), (6, 8192, 13, 2),
