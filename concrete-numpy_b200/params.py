@@ -146,6 +146,16 @@ WIDE_SHAPES = ((1, 2048), (1, 4096), (2, 1024), (3, 512))      # (k, N) candidat
 WIDE_SHAPE_EFFICIENCY = {(1, 2048): 1.0, (1, 4096): 0.9, (2, 1024): 0.5, (3, 512): 0.36}
 
 
+def wide_efficiency(k: int, N: int, pbs_level: int) -> float:
+    """... and by decomposition depth: up to two levels the N = 2048 bootstrap runs the grouped kernel (two ciphertext slots
+    per SM, 12.1 TFLOP/s); deeper decompositions leave room for one ciphertext per SM only and run the generic kernel
+    (8.3 TFLOP/s at three levels; scripts/group_ablation.py, profiles/r02_group_ablation.log)."""
+    eff = WIDE_SHAPE_EFFICIENCY.get((k, N), 0.5)
+    if (k, N) == (1, 2048) and pbs_level >= 3:
+        eff *= 0.69
+    return eff
+
+
 @lru_cache(maxsize=None)
 def select_parameters(p: int, norm2: float = 1.0, p_error: float = 1e-9) -> CryptoParams:
     """Cheapest parameter set meeting `p_error` per table lookup at precision p."""
@@ -359,7 +369,7 @@ def select_wide_parameters(p: int, norm2: float = 1.0, p_error: float = 1e-9,
                             if not np.any(ok):
                                 continue
                             cost = np.where(ok, base_cost + T * KS_MAC_COST * kN * (ks_level - 1) * (n_grid + 1), np.inf)
-                            cost = cost / WIDE_SHAPE_EFFICIENCY.get((k, N), 0.5)
+                            cost = cost / wide_efficiency(k, N, pbs_level)
                             j = int(np.argmin(cost))
                             if best is None or cost[j] < best[0]:
                                 best = (float(cost[j]), int(n_grid[j]), k, N, pbs_level, pbs_base_log, ks_level, ks_base_log,
