@@ -7,7 +7,9 @@ from concrete_numpy_b200 import engine as E, params as P
 name, B = sys.argv[1], int(sys.argv[2])
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 dev = torch.device("cuda:0")
-p = P.REFERENCE_SETS[int(name[1:])]
+P5 = E.CryptoParams(p=5, n=786, k=1, N=4096, pbs_level=2, pbs_base_log=13, ks_level=5, ks_base_log=3,
+                    lwe_std=2.0 ** -20, glwe_std=2.0 ** -50)          # the set the backend selects for cfg5
+p = P5 if name == "p5" else P.REFERENCE_SETS[int(name[1:])]
 ks = E.KeySet(p, dev, seed=42)
 ev = E.EvalKeys.of(ks)
 rng = np.random.default_rng(0)
