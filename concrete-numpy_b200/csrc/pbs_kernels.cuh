@@ -677,7 +677,7 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
       const double2* __restrict__ twT, const double2* __restrict__ tw_mid, long long* prof, size_t bsk_ct_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int C = P::C, R1 = P::R1, NT = P::NT, RF = P::RF, BUF = P::BUF, Q = P::Q, S = P::S;
-    constexpr int N = P::N, M = P::M;
+    constexpr int N = P::N;
     // optional phase timing (development aid, fhe_pbs_set_profile): thread 0 of CTA 0 accumulates
     // clock64() deltas per phase
     // (CTA b < 16 writes prof[16*b + slot]: CTA 0 is the reference, the others show the skew inside cluster 0)
@@ -892,7 +892,6 @@ k_pbs(u64* __restrict__ out, const u64* __restrict__ in, long B, const double2* 
                 csync<C>();
             PBS_PROF(5)
             // ---- P5: gather from owners, inverse radix-R1 stage, untwist, round, ACC +=
-#pragma unroll 1
             int o_ready = -1;
             for (int it = tid; it < ((k + 1) << P::LOGQ); it += NT) {
                 const int o = it >> P::LOGQ, q = it & (Q - 1);
