@@ -257,7 +257,11 @@ class EvalKeys:
         A circuit has a handful of distinct batch sizes; each costs a few tens of milliseconds once per key set."""
         p = self.params
         dev = self.bsk_f.device
-        small = torch.zeros((count, p.n + 1), dtype=torch.int64, device=dev)
+        # random mask words: the rotation amounts decide which CTA every accumulator word is pushed to (all-zero inputs would
+        # keep the cluster exchange of the pipelined plans local and flatter them)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(0x5eed)
+        small = torch.randint(-(1 << 62), 1 << 62, (count, p.n + 1), dtype=torch.int64, device=dev, generator=gen)
         luts = torch.zeros((1, (p.k + 1) * p.N), dtype=torch.int64, device=dev)
         out = torch.empty((count, p.ct_words), dtype=torch.int64, device=dev)
         best, best_ms = 0, float("inf")
