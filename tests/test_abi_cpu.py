@@ -108,6 +108,16 @@ def test_plan_selection_and_python_mirror():
                     sizes = [lib.fhe_pbs_variant_cluster_size(1 << logN, k, level, v) for v in range(nv)]
                     assert sizes == sorted(sizes) and sizes[0] == c == plan(1 << logN, k, level)[0]
     assert lib.fhe_pbs_variant_plan(2048, 1, 1, 99, (C.c_int * 8)()) != 0
+    # which kernels serve which plan (round 2): N = 2048 up to two levels = the grouped kernel with two ciphertext slots per CTA,
+    # N = 4096 = its single-slot 512-thread plan (radix 8 x 8 x 4 x 8), the 2048-point cluster plans and the 4-CTA latency plan
+    # of N = 4096 = the pipelined kernel (two levels only)
+    assert [lib.fhe_pbs_variant_grouped(2048, 1, lv, 0) for lv in (1, 2, 3, 4)] == [1, 1, 0, 0]
+    assert lib.fhe_pbs_variant_grouped(2048, 2, 1, 0) <= 0 and lib.fhe_pbs_variant_grouped(2048, 1, 1, 99) < 0
+    assert plan(4096, 1, 2) == (1, 3, 3, 2, 3, 512, 1, 1) and lib.fhe_pbs_variant_grouped(4096, 1, 2, 0) == 0
+    assert [lib.fhe_pbs_variant_pipelined(N, 1, 2, 0) for N in (32768, 16384, 8192, 4096, 2048)] == [1, 1, 1, 0, 0]
+    assert lib.fhe_pbs_variant_pipelined(32768, 1, 3, 0) == 0
+    clusters = [lib.fhe_pbs_variant_cluster_size(4096, 1, 2, v) for v in range(lib.fhe_pbs_num_variants(4096, 1, 2))]
+    assert [lib.fhe_pbs_variant_pipelined(4096, 1, 2, v) for v in range(len(clusters))] == [int(c == 4) for c in clusters]
 
 
 def test_key_material_and_cache_file_mode(oracle, tmp_path):
