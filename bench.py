@@ -425,6 +425,12 @@ def run_ours(args):
             n_pbs_ = int(circ.server._feedback.n_pbs)
             entry = {"latency_ms": t_ms, "n_pbs": n_pbs_, "pbs_per_s": n_pbs_ / (t_ms * 1e-3),
                      "decrypted_output_correct": ok_, "params": params_brief(p_)}
+            if fp64_peak:
+                # whole-circuit fp64 roofline fraction: the bootstraps' algorithmic flops over the circuit's
+                # device time (keyswitches, linear kernels and partial waves included) over the measured DFMA peak
+                tf_ = n_pbs_ * flops_per_pbs(p_) / (t_ms * 1e-3) / 1e12
+                entry["roofline"] = {"bound": "fp64", "achieved": tf_, "peak": fp64_peak, "unit": "TFLOP/s",
+                                     "frac": tf_ / fp64_peak, "flops_per_pbs": flops_per_pbs(p_)}
             if lin is not None and name.startswith(("cfg3", "cfg4")):
                 entry["linear_kernel"] = lin
             if cores:
