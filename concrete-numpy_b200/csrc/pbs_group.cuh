@@ -6,10 +6,11 @@
 //   * the CTA has G * NT threads; slot `grp` is run by threads [grp*NT, (grp+1)*NT) with the phases, the FFT factorisation
 //     and the Fourier key layout of k_pbs, synchronised by its own named barrier (bar.sync grp+1, NT), so the slots drift
 //     out of phase like independent CTAs do and overlap each other's FP64- and shared-memory-bound phases;
-//   * one CTA per SM owns all of tensor memory: the mid-pass twiddles and the stage-1 twiddles of a thread's item live in
-//     its tensor-memory lane (fetched 4 at a time: the kernel runs at 128 registers), which takes a fifth of the traffic
-//     off the shared-memory pipe -- the co-bottleneck of these shapes (ncu: shared-memory wavefronts 62 %, issue slots 62 %,
-//     FP64 pipe 46 % of peak);
+//   * one CTA per SM owns all of tensor memory: the mid-pass twiddles, the stage-1 twiddles of a thread's item and the
+//     item's own accumulator words (read in P1, updated in P5 by the same thread; the shared array remains the copy the
+//     ROTATED operand is read from) live in its tensor-memory lane (twiddles fetched 4 at a time: the kernel runs at 128
+//     registers), which takes a quarter of the traffic off the shared-memory pipe -- the most loaded resource of these
+//     shapes (ncu: shared-memory wavefronts 56 %, issue slots 61 %, FP64 pipe 47 % of peak before the accumulator moved);
 //   * RING = true (the north star's "each GGSW row staged once ... reused across the batch"): GGSW_i lives in a ring of
 //     (k+1)*J slices of BUF double2, every slice ONE bulk asynchronous copy global -> shared (cp.async.bulk, completion on
 //     the slice's mbarrier).  A warp that has taken its values of a slice counts itself off on the slice's counter; the
@@ -40,7 +41,8 @@ template <class P, int G>
 struct PbsGroup {
     static constexpr int NTC = P::NT * G;                       // threads per CTA
     // tensor-memory columns per thread: mid-pass twiddles + the R1 stage-1 twiddles of the thread's one item
-    static constexpr int TM_T = P::TM_A + P::TM_B + 4 * P::R1;
+    // ... and its 2 * R1 own accumulator words (the same thread reads them in P1 and updates them in P5)
+    static constexpr int TM_T = P::TM_A + P::TM_B + 4 * P::R1 + 4 * P::R1;
     static constexpr int TM_NEED = TM_T * ((NTC + 127) / 128);
     static constexpr int TM_COLS = TM_NEED <= 32 ? 32 : TM_NEED <= 64 ? 64 : TM_NEED <= 128 ? 128 : TM_NEED <= 256 ? 256 : 512;
     static constexpr int MAX_SLICES = 8;                        // (k+1) * J with k = 1, level <= 4
@@ -124,8 +126,8 @@ k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const dou
     tw.base = s_tmem_base;
     tw.tA = tw.base + ((unsigned)((((int)threadIdx.x >> 5) & 3) * 32) << 16) + (unsigned)(((int)threadIdx.x >> 7) * GP::TM_T);
     tw.tB = tw.tA + P::TM_A;
-    tw.tAcc = 0;
     tw.tT = tw.tB + P::TM_B;
+    tw.tAcc = tw.tT + 4 * P::R1;
     {
         double2 T[R1];
         load_T<P>(T, tw, tid & (P::Q - 1));
@@ -157,6 +159,20 @@ k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const dou
             }
         }
         group_sync(bar_id, NT);
+        {
+            // the thread's own words (item tid: polynomial tid >> LOGQ, slot q) -> its tensor-memory lane; the shared array
+            // stays the copy the ROTATED operand is read from
+            const u64* accc = acc + ((size_t)(tid >> P::LOGQ) << P::LOGS) + (tid & (P::Q - 1));
+            unsigned ow[4 * R1];
+#pragma unroll
+            for (int hj = 0; hj < 2 * R1; hj++) {
+                const u64 v = accc[hj << P::LOGQ];
+                ow[2 * hj] = (unsigned)v;
+                ow[2 * hj + 1] = (unsigned)(v >> 32);
+            }
+            TmemIo<4 * R1>::st(tw.tAcc, ow);
+            tmem_wait_st();
+        }
 
         for (int i = 0; i < g.n; i++, it++) {
             const int a = a_next;
@@ -165,9 +181,9 @@ k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const dou
                 prefetch_l2_bulk(bskF + (size_t)(i + 1) * ggsw_stride + ((size_t)tid << P::LOGBUF), BUF_BYTES);
             // ---- P1: rotate, subtract, decompose, fold + twist, radix-R1 stage
             if (level * base_log <= 30)
-                p1_items<P, unsigned, true>(acc, work, 0, a, g, tw, tid);
+                p1_items<P, unsigned, true, true>(acc, work, 0, a, g, tw, tid);
             else
-                p1_items<P, u64, true>(acc, work, 0, a, g, tw, tid);
+                p1_items<P, u64, true, true>(acc, work, 0, a, g, tw, tid);
             group_sync(bar_id, NT);
             GROUP_PROF(0)
             // ---- P2: forward mid passes of the J digit polynomials
@@ -264,11 +280,21 @@ k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const dou
                 stage1_gather<P>(work + ((size_t)o << P::LOGBUF), q, T, g, z);
                 u64* acco = acc + ((size_t)o << P::LOGS);
 #pragma unroll
-                for (int j1 = 0; j1 < R1; j1++) {
-                    acco[(j1 << P::LOGQ) + q] += f2torus_frac(z[j1].x, tscale);
-                    acco[((R1 + j1) << P::LOGQ) + q] += f2torus_frac(z[j1].y, tscale);
+                for (int half = 0; half < 2; half++) {
+                    unsigned ow[2 * R1];
+                    TmemIo<2 * R1>::ld(tw.tAcc + (unsigned)(half * 2 * R1), ow);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j1 = 0; j1 < R1; j1++) {
+                        const u64 v = (((u64)ow[2 * j1 + 1] << 32) | (u64)ow[2 * j1]) + f2torus_frac(half ? z[j1].y : z[j1].x, tscale);
+                        ow[2 * j1] = (unsigned)v;
+                        ow[2 * j1 + 1] = (unsigned)(v >> 32);
+                        acco[((half * R1 + j1) << P::LOGQ) + q] = v;          // the copy the next rotation reads
+                    }
+                    TmemIo<2 * R1>::st(tw.tAcc + (unsigned)(half * 2 * R1), ow);
                 }
             }
+            tmem_wait_st();
             group_sync(bar_id, NT);
             GROUP_PROF(6)
         }

@@ -567,7 +567,9 @@ __device__ __forceinline__ size_t ggsw_slice(int j, int o, int k, int rank) {
 // ---- P1 of a CMUX for every item (c, q) of this CTA: diff = X^a * ACC - ACC, signed decomposition
 // (closest representable, balanced digits), one stage-1 emit per level.  ST = u32 when the kept
 // level*base_log bits fit 30 bits (halves the registers of the decomposition state).
-template <class P, typename ST, bool TMT = false>
+// OWN_TM (k_pbs_group): the thread's own accumulator words wait in its tensor-memory lane (TwCtx::tAcc, one item per
+// thread); the rotated operand still comes from the shared-memory copy
+template <class P, typename ST, bool TMT = false, bool OWN_TM = false>
 __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* __restrict__ work, int rank, int a,
                                          const PbsGeom& g, const TwCtx& tw,
                                          int tix = -1 /* thread index inside the NT threads of this ciphertext (default: threadIdx.x) */) {
@@ -599,7 +601,8 @@ __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* _
 #pragma unroll
             for (int half = 0; half < 2; half++) {       // two batches bound the registers in flight
                 u64 rv[R1];
-                unsigned ow[P::ACC_TM ? 2 * R1 : 1];
+                unsigned ow[(P::ACC_TM || OWN_TM) ? 2 * R1 : 1];
+                if constexpr (OWN_TM) TmemIo<2 * R1>::ld(tw.tAcc + (unsigned)(half * 2 * R1), ow);
                 if constexpr (P::ACC_TM) {
                     // the rotated operand was pushed into `acc` by its producers (sign applied), the thread's own
                     // words wait in its tensor-memory lane: no remote access on this side of the exchange
@@ -614,6 +617,7 @@ __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* _
                         if (C > 1) rv[e] = ld_cluster_u64(src_peer + ((unsigned)hjp << (P::LOGQ + 3)));
                         else rv[e] = src_local[hjp << P::LOGQ];
                     }
+                    if constexpr (OWN_TM) tmem_wait_ld();
                 }
 #pragma unroll
                 for (int e = 0; e < R1; e++) {
@@ -623,7 +627,9 @@ __device__ __forceinline__ void p1_items(const u64* __restrict__ acc, double2* _
                     if constexpr (P::ACC_TM) {
                         diff = rv[e] - (((u64)ow[2 * e + 1] << 32) | (u64)ow[2 * e]);
                     } else {
-                        const u64 own = accc[(hj << P::LOGQ) + q];
+                        u64 own;
+                        if constexpr (OWN_TM) own = ((u64)ow[2 * e + 1] << 32) | (u64)ow[2 * e];
+                        else own = accc[(hj << P::LOGQ) + q];
                         diff = ((hjr >> (P::LOGR1 + 1)) ? (0ULL - rv[e]) : rv[e]) - own;
                     }
                     if (sizeof(ST) == 4) {
