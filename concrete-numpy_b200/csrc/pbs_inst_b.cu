@@ -14,7 +14,8 @@ static const PbsPlanEntry g_entries[] = {
     // M = 1024, 2 x 256 threads per SM at 128 registers (16 warps per SM); one- and two-level bootstraps run k_pbs_group: ONE
     // CTA per SM with two ciphertext slots, twiddles in tensor memory
     PBS_PLAN_ENTRY(PbsPlan<1, 3, 4, 0, 3, 256, 2, 1, 0, 2>),
-    PBS_PLAN_ENTRY(PbsPlan<1, 3, 4, 0, 3, 256, 1, 1>),   // M = 1024 with >= 3 levels (one CTA per SM by shared memory): 8 warps instead of 4
+    // M = 1024 with >= 3 levels (one CTA per SM by shared memory): 8 warps instead of 4; k = 1 runs k_pbs_group with one slot
+    PBS_PLAN_ENTRY(PbsPlan<1, 3, 4, 0, 3, 256, 1, 1, 0, 1>),
 };
 const PbsPlanEntry* pbs_plans_b(int* count) {
     *count = (int)(sizeof(g_entries) / sizeof(g_entries[0]));

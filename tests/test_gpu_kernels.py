@@ -351,8 +351,8 @@ def test_grouped_bootstrap_is_bit_identical_to_the_generic_kernel(cuda_device, B
     stages it once per SM by bulk copies into a shared-memory ring read by both) performs the floating-point operations of
     k_pbs in the same order: every output WORD must be equal (fhe_pbs_set_group switches at run time).  The batch sizes
     cover one slot per CTA, ragged second slots, and several rounds with a ragged last one (the ring runs on across
-    rounds).  With two levels the GGSW does not fit next to two ciphertexts (mode 2 streams as well); three levels run
-    another plan (the switch is a no-op there)."""
+    rounds).  With two levels the GGSW does not fit next to two ciphertexts (mode 2 streams as well); with three levels only
+    one ciphertext fits an SM: that plan runs the grouped kernel with a single 256-thread slot."""
     stress = os.environ.get("CNP_B200_STRESS", "0") not in ("", "0")
     n = 742 if stress else 96
     p = E.CryptoParams(p=4, n=n, k=1, N=2048, pbs_level=level, pbs_base_log=base_log, ks_level=5, ks_base_log=3,
