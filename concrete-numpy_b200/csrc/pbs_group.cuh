@@ -104,8 +104,8 @@ k_pbs_group(u64* __restrict__ out, const u64* __restrict__ in, long B, const dou
     {
         const int warp = (int)threadIdx.x >> 5;
         if (warp == 0) tmem_alloc(&s_tmem_base, GP::TM_COLS);
-        if (threadIdx.x == 0) {
-            for (int s = 0; s < nslices; s++) {
+        if (RING && threadIdx.x == 0) {          // the ring's barriers and counters (RING implies nslices <= MAX_SLICES)
+            for (int s = 0; s < nslices && s < GP::MAX_SLICES; s++) {
                 mbar_init(&s_full[s], 1);
                 s_cnt[s] = 0;
             }

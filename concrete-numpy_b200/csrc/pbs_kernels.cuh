@@ -1394,7 +1394,7 @@ struct PbsPlanOps {
             const bool ext = a.bsk_ct_stride || a.g.nout > 1 || a.g.theta > 0;
             // g_pbs_group: 1 = two slots per CTA, GGSW_i streamed from L2 (default: measured fastest); 2 = GGSW_i staged once
             // per SM in the shared-memory ring when it fits (north-star design, measured 4 % slower); 0 = k_pbs
-            const bool ring = g_pbs_group == 2 && !ext && GP::smem(a.g, true) + 2048 <= PBS_SMEM_MAX;
+            const bool ring = g_pbs_group == 2 && !ext && 2 * a.g.J <= GP::MAX_SLICES && GP::smem(a.g, true) + 2048 <= PBS_SMEM_MAX;
             if (g_pbs_group != 0 && a.g.k == 1 && GP::smem(a.g, ring) + 2048 <= PBS_SMEM_MAX) {
                 if (ring)
                     return launch_grouped(k_pbs_group<P, P::GROUP, true, false>, GP::NTC, GP::smem(a.g, true), a.B, a.st, a.out,

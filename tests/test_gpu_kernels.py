@@ -345,7 +345,7 @@ def test_pipelined_bootstrap_is_bit_identical_to_the_generic_kernel(cuda_device,
 
 
 @pytest.mark.parametrize("B,level,base_log", [(1, 1, 23), (100, 1, 23), (148, 1, 23), (149, 1, 23), (296, 1, 23),
-                                              (300, 1, 23), (1000, 1, 23), (300, 2, 12), (449, 3, 8)])
+                                              (300, 1, 23), (1000, 1, 23), (300, 2, 12), (449, 3, 8), (200, 4, 6)])
 def test_grouped_bootstrap_is_bit_identical_to_the_generic_kernel(cuda_device, B, level, base_log):
     """k_pbs_group (pbs_group.cuh: one CTA per SM carries two N = 2048 ciphertexts; mode 1 streams GGSW_i from L2, mode 2
     stages it once per SM by bulk copies into a shared-memory ring read by both) performs the floating-point operations of
